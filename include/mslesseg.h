@@ -1,0 +1,173 @@
+/*
+ * mslesseg.h - C ABI of libmslesseg.so, the B200 (sm_100a) implementation of the voxel-level
+ * volume path of srozenblum/YOLO-MSLesSeg.
+ *
+ * The reference is pure Python and has no FFI of its own: the seam is a set of Python call
+ * sites.  Each entry point below names the reference function(s) whose arithmetic it replaces
+ * (paths relative to the reference checkout).  INTEGRATION.md shows the ctypes binding a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *  - Every data pointer is a DEVICE pointer owned by the caller (e.g. a torch CUDA tensor).  The
+ *    library allocates nothing, frees nothing and keeps no state except a thread-local error string.
+ *  - Work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *    default stream).  The caller synchronises.
+ *  - Return value: MSL_OK (0) or a negative MSL_ERR_* code; msl_last_error() describes the failure.
+ *  - Volumes are C-contiguous [nvol][Z][Y][X] (x fastest) - byte-identical to the Fortran-ordered
+ *    (X, Y, Z) array nibabel's get_fdata() yields (reference utils/Paciente.py:168).
+ *  - Slice orientation ("G"): the 2-D array the reference sees, S.shape = (rows, cols):
+ *       axial   S[x, y] = V[x, y, k]   (rows, cols) = (X, Y)     utils/Paciente.py:240
+ *       coronal S[x, z] = V[x, j, z]   (rows, cols) = (X, Z)     utils/Paciente.py:241
+ *       sagital S[y, z] = V[i, y, z]   (rows, cols) = (Y, Z)     utils/Paciente.py:242
+ *    PNG orientation ("P"): what scripts/extraer_dataset.py:192 saves, imsave(G.T, origin="lower"):
+ *       P[r, c] = G[c, cols-1-r],  P.shape = (cols, rows).
+ */
+#ifndef MSLESSEG_H
+#define MSLESSEG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSL_ABI_VERSION 1
+
+#define MSL_OK               0
+#define MSL_ERR_ARG         -1   /* NULL pointer, bad enum, non-positive size, bad pitch        */
+#define MSL_ERR_UNSUPPORTED -2   /* combination not implemented (see each function)           */
+#define MSL_ERR_CUDA        -3   /* a CUDA runtime call failed; message holds cudaGetErrorString */
+#define MSL_ERR_WORKSPACE   -4   /* workspace missing or smaller than msl_workspace_bytes()    */
+
+/* planes - reference utils/Paciente.py:68 PLANOS */
+#define MSL_AXIAL   0
+#define MSL_CORONAL 1
+#define MSL_SAGITAL 2
+
+/* enhancements - reference utils/Paciente.py:67 MEJORAS, utils/mejora_imagen.py */
+#define MSL_MEJORA_NONE  0
+#define MSL_MEJORA_HE    1   /* mejora_imagen.py:52-67   == cv2.equalizeHist on the normalised slice */
+#define MSL_MEJORA_CLAHE 2   /* mejora_imagen.py:91-117  == LUT_OUT[clahe_8x8_clip2(LUT_L[u])]        */
+#define MSL_MEJORA_GC    3   /* mejora_imagen.py:139-151 == GC_T[u]                                   */
+#define MSL_MEJORA_LT    4   /* mejora_imagen.py:166-184 == LT_T[max u][u]                            */
+
+/* element type of an input image / volume */
+#define MSL_F32 0
+#define MSL_U8  1
+
+/* output layouts of the enhance entry points */
+#define MSL_OUT_G        0   /* gray slice, slice orientation (rows, cols), 1 byte / pixel           */
+#define MSL_OUT_P        1   /* gray slice, PNG orientation (cols, rows), 1 byte / pixel             */
+#define MSL_OUT_PNG_GRAY 2   /* imsave(cmap="gray") gray byte, PNG orientation, 1 byte / pixel (E8)  */
+#define MSL_OUT_PNG_RGBA 3   /* imsave RGBA pixels, PNG orientation, 4 bytes / pixel (E8)            */
+
+/* Constant tables, one caller-owned device buffer of MSL_TABLES_BYTES bytes:
+ *   [0    ,  256)  LUT_L    gray -> Lab L            (cv2 GRAY2BGR + BGR2LAB,  mejora_imagen.py:98,101)
+ *   [256  ,  512)  LUT_OUT  L'   -> gray             (cv2 LAB2BGR + BGR2GRAY,  mejora_imagen.py:112,115; utils.py:426)
+ *   [512  ,  768)  GC_T     gamma table              (mejora_imagen.py:146)
+ *   [768  , 1024)  CM       matplotlib gray colormap bytes (extraer_dataset.py:192)
+ *   [1024 , 1024+65536) LT_T[m][v]  log table for a slice whose maximum is m (mejora_imagen.py:173-182)
+ * They are parameters computed on the host with the reference's own NumPy expressions
+ * (mslesseg_b200/tables.py); the library only reads them. */
+#define MSL_TAB_LUT_L   0
+#define MSL_TAB_LUT_OUT 256
+#define MSL_TAB_GC      512
+#define MSL_TAB_CM      768
+#define MSL_TAB_LT      1024
+#define MSL_TABLES_BYTES (1024 + 65536)
+
+/* workspace kinds for msl_workspace_bytes() */
+#define MSL_WS_ENHANCE_VOLUMES 1
+#define MSL_WS_RECON           2
+
+typedef void* msl_stream_t;   /* cudaStream_t */
+
+int         msl_version(void);
+const char* msl_last_error(void);
+
+/* Bytes of scratch the caller must pass as `ws` to the entry point `op` (MSL_WS_*). */
+size_t msl_workspace_bytes(int op, int nvol, int X, int Y, int Z);
+
+/* ---- E0: lesion-slice flags -------------------------------------------------------------------
+ * Replaces the `np.any(mask_slice > 0)` loop of Paciente.indices_cortes_con_lesion
+ * (utils/Paciente.py:252-259) for all three planes in one pass over the mask.
+ * gt: [nvol][Z][Y][X], dtype MSL_U8 or MSL_F32.  any_ax[nvol][Z], any_co[nvol][Y], any_sa[nvol][X]
+ * receive 1 where the slice holds a voxel > 0, else 0.  The index-window arithmetic of
+ * indices_a_usar (:261-275) and the percentile (scripts/extraer_dataset.py:110-135) stay on the host. */
+int msl_lesion_slices(const void* gt, int dtype, int nvol, int X, int Y, int Z,
+                      uint8_t* any_ax, uint8_t* any_co, uint8_t* any_sa, msl_stream_t stream);
+
+/* ---- E1-E8: enhance a list of slices of resident volumes ------------------------------------
+ * Replaces, per slice, Paciente.obtener_corte_imagen (utils/Paciente.py:216-222) ->
+ * aplicar_mejora (:195-210) -> <HE|CLAHE|GC|LT>.aplicar (utils/mejora_imagen.py) incl.
+ * convertir_a_bgr / normalizar_a_uint8 (utils/utils.py:396-418), verificar_grises
+ * (utils/utils.py:421-427, called at scripts/extraer_dataset.py:190) and, for the PNG layouts,
+ * the orientation + matplotlib normalisation / colormap of guardar_cortes (extraer_dataset.py:192,197).
+ *
+ * vol: [nvol][Z][Y][X] of `dtype`.  Slice s is plane `plano`, volume vol_of_slice[s], index
+ * idx_of_slice[s] (device int32 arrays; both NULL = dense: every index of every volume,
+ * s = v * n_plane + i, and nslices must equal nvol * n_plane).  Entries outside the volume are
+ * skipped.  Output slice s starts at out + s * slice_pitch_bytes.
+ * Supported: mejora HE/CLAHE/GC/LT with any layout; mejora NONE with dtype U8 and any layout
+ * (mask slices) or dtype F32 and a PNG layout (imsave of the raw slice, float64 normalisation).
+ * MSL_F32 input is normalised per slice exactly like normalizar_a_uint8; MSL_U8 input is used as is. */
+int msl_enhance_slices(const void* vol, int dtype, int nvol, int X, int Y, int Z,
+                       int mejora, int plano,
+                       const int32_t* vol_of_slice, const int32_t* idx_of_slice, int nslices,
+                       uint8_t* out, size_t slice_pitch_bytes, int layout,
+                       const uint8_t* tables, msl_stream_t stream);
+
+/* ---- E1-E8 on stand-alone 2-D images --------------------------------------------------------
+ * Replaces Algoritmo.aplicar(imagen) + verificar_grises for a batch of C-contiguous 2-D images
+ * (utils/mejora_imagen.py:31,52,91,139,166).  imgs: [nimg] images of rows x cols elements,
+ * image n at imgs + n * img_pitch_elems elements. */
+int msl_enhance_images(const void* imgs, int dtype, int nimg, int rows, int cols, size_t img_pitch_elems,
+                       int mejora, uint8_t* out, size_t out_pitch_bytes, int layout,
+                       const uint8_t* tables, msl_stream_t stream);
+
+/* ---- E1-E7 whole volumes, all three planes from one resident copy ----------------------------
+ * Same results as msl_enhance_slices(dense) for every plane, produced by a tri-planar pipeline
+ * (per-slice min/max of the three planes in one pass, normalise + scatter, per-slice HE/CLAHE).
+ * outs: HOST array of 12 DEVICE pointers indexed (mejora-1)*3 + plano; NULL = not wanted.
+ * outs[(m-1)*3+p] receives [nvol][n_p] slices in PNG orientation (MSL_OUT_P), densely packed.
+ * ws: msl_workspace_bytes(MSL_WS_ENHANCE_VOLUMES, ...) bytes of device scratch. */
+int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z,
+                        uint8_t* const* outs, const uint8_t* tables,
+                        void* ws, size_t ws_bytes, msl_stream_t stream);
+
+/* ---- R1-R2: stack predicted 2-D masks back into volumes ---------------------------------------
+ * Replaces cargar_y_preprocesar_imagen's binarisation (scripts/reconstruir_volumen.py:146-148),
+ * insertar_corte (:179-186) and the zero-initialised volume of reconstruir_volumen (:199-213).
+ * slices: uint8 pred masks in slice orientation (rows, cols), slice s at slices + s*slice_pitch_bytes;
+ * voxel = (pixel > 0).  Indices never listed stay 0; validar_corte's range/shape checks (:153-176)
+ * are done by the host wrapper, out-of-range entries are skipped here.  If an index is listed
+ * twice the slice with the larger s wins.  At least one of vol_u8 / vol_f32 ([nvol][Z][Y][X]) must
+ * be non-NULL.  ws: msl_workspace_bytes(MSL_WS_RECON, ...). */
+int msl_recon(const uint8_t* slices, size_t slice_pitch_bytes,
+              const int32_t* vol_of_slice, const int32_t* idx_of_slice, int nslices, int plano,
+              int nvol, int X, int Y, int Z, uint8_t* vol_u8, float* vol_f32,
+              void* ws, size_t ws_bytes, msl_stream_t stream);
+
+/* ---- R3-R4: tri-planar vote fused with the voxel confusion counts -----------------------------
+ * Replaces combinar_volumenes (scripts/generar_consenso.py:106-109): consenso = (ax+co+sa >= umbral),
+ * and the boolean sums behind DSC / precision / recall / AUC (utils/utils.py:455-495) for the three
+ * planes and the consensus in ONE pass.  All volumes uint8 [nvol][nvox].
+ * counts: int64 [nvol][4][4] = {axial, coronal, sagital, consenso} x {tp, fp, fn, tn} with the
+ * reference's exact predicates (gt==1 & p==1, gt==0 & p==1, gt==1 & p==0, gt==0 & p==0); the
+ * buffer is overwritten.  tp+fp+fn+tn < nvox reveals non-binary input to the host.
+ * gt and counts may both be NULL (vote only); consenso may be NULL (counts only). */
+int msl_consensus_eval(const uint8_t* ax, const uint8_t* co, const uint8_t* sa, const uint8_t* gt,
+                       int nvol, size_t nvox, int umbral,
+                       uint8_t* consenso, int64_t* counts, msl_stream_t stream);
+
+/* ---- R4 for one prediction volume per patient -----------------------------------------------
+ * Replaces the sums of generar_diccionario_metricas(gt_vol, pred_vol) (scripts/eval.py:115-128).
+ * counts: int64 [nvol][4] = {tp, fp, fn, tn}, overwritten. */
+int msl_confusion_counts(const uint8_t* gt, const uint8_t* pred, int nvol, size_t nvox,
+                         int64_t* counts, msl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSLESSEG_H */

@@ -1,0 +1,303 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (mslesseg_b200.ops ->
+libmslesseg.so), against the golden vectors frozen from the real reference and against the CPU
+oracle on the same seeded inputs.  Bar: bit-exact for every uint8 / mask / count output."""
+import hashlib
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from mslesseg_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+PLANOS = O.PLANOS
+MEJORAS = O.MEJORAS
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def ops(cuda_device):
+    from mslesseg_b200 import ops as _ops
+    from mslesseg_b200 import _lib
+    _lib.load()
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def torch_mod(cuda_device):
+    import torch
+    return torch
+
+
+def oracle_all(vol_xyz, plano, mejora):
+    n = vol_xyz.shape[O.plane_axis(plano)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return np.stack([O.enhance_slice(O.slice_of(vol_xyz, plano, i), mejora) for i in range(n)])
+
+
+def explain(got, want, tag):
+    bad = [i for i in range(len(want)) if not np.array_equal(got[i], want[i])]
+    npx = int((got != want).sum())
+    return f"{tag}: {len(bad)} slices differ (first {bad[:5]}), {npx} pixels"
+
+
+# ------------------------------------------------------------------------------ input side
+def test_demo_slices_golden(ops, torch_mod, demo_slices, cuda_device):
+    torch = torch_mod
+    for k in [k for k in demo_slices.files if k.endswith("_raw")]:
+        raw = torch.from_numpy(demo_slices[k].astype(np.float32)).to(cuda_device)[None].contiguous()
+        for mej in MEJORAS:
+            got = ops.enhance_images(raw, mej, layout="G")[0].cpu().numpy()
+            want = demo_slices[k[:-4] + "_" + mej]
+            assert np.array_equal(got, want), (k, mej, int((got != want).sum()))
+
+
+@pytest.mark.parametrize("pid", ["P1", "P2"])
+def test_synthetic_volume_slice_mode_golden(ops, torch_mod, golden, cuda_device, pid):
+    torch = torch_mod
+    g = golden["synthetic_enhance"][pid]
+    pat = S.make_patient(int(pid[1:]), config_id=1, num_cortes=20)
+    assert sha(pat.flair) == g["flair_sha"]
+    vol = torch.from_numpy(pat.flair).to(cuda_device)[None].contiguous()
+    vxyz = S.as_xyz(pat.flair).astype(np.float64)
+    for plano in PLANOS:
+        for mej in MEJORAS:
+            got = ops.enhance_slices(vol, mej, plano, layout="G").cpu().numpy()
+            if sha(got) != g["planes"][plano][mej]:
+                pytest.fail(explain(got, oracle_all(vxyz, plano, mej), f"{pid} {plano} {mej}"))
+
+
+@pytest.mark.parametrize("pid", ["P1", "P2"])
+def test_synthetic_volume_mode_golden(ops, torch_mod, golden, cuda_device, pid):
+    torch = torch_mod
+    g = golden["synthetic_enhance"][pid]
+    pat = S.make_patient(int(pid[1:]), config_id=1, num_cortes=20)
+    vol = torch.from_numpy(pat.flair).to(cuda_device)[None].contiguous()
+    res = ops.enhance_volumes(vol)
+    vxyz = S.as_xyz(pat.flair).astype(np.float64)
+    for plano in PLANOS:
+        for mej in MEJORAS:
+            P = res[(mej, plano)][0]                       # [n_p, cols, rows]
+            G = P.flip(-2).transpose(-1, -2).contiguous().cpu().numpy()
+            if sha(G) != g["planes"][plano][mej]:
+                pytest.fail(explain(G, oracle_all(vxyz, plano, mej), f"{pid} {plano} {mej} (volume mode)"))
+
+
+def test_volume_mode_batch_and_subsets(ops, torch_mod, cuda_device):
+    torch = torch_mod
+    pats = [S.make_patient(n, config_id=1, with_predictions=False) for n in (3, 4, 5, 6, 7)]
+    vol = torch.from_numpy(np.stack([p.flair for p in pats])).to(cuda_device)
+    full = ops.enhance_volumes(vol)
+    # subsets must give the same bytes as the full call, and slice mode must agree with volume mode
+    sub = ops.enhance_volumes(vol, mejoras=("CLAHE",), planos=("sagital",))
+    assert torch.equal(sub[("CLAHE", "sagital")], full[("CLAHE", "sagital")])
+    sub = ops.enhance_volumes(vol, mejoras=("GC", "LT"), planos=("coronal", "axial"))
+    for k, t in sub.items():
+        assert torch.equal(t, full[k]), k
+    for mej in MEJORAS:
+        for plano in PLANOS:
+            ref = ops.enhance_slices(vol, mej, plano, layout="P")
+            assert torch.equal(ref.view_as(full[(mej, plano)]), full[(mej, plano)]), (mej, plano)
+
+
+def _noise(seed, shape_xyz):
+    from oracle.make_golden import noise_volume
+    return noise_volume(seed, shape_xyz)
+
+
+def test_noise_volume_golden(ops, torch_mod, golden, cuda_device):
+    torch = torch_mod
+    g = golden["noise_enhance"]
+    nv = _noise(g["seed"], tuple(g["shape_xyz"]))
+    assert sha(nv) == g["in_sha"]
+    vol = torch.from_numpy(nv).to(cuda_device)[None].contiguous()
+    res = ops.enhance_volumes(vol)
+    vxyz = S.as_xyz(nv).astype(np.float64)
+    for plano in PLANOS:
+        for mej in MEJORAS:
+            got = ops.enhance_slices(vol, mej, plano, layout="G").cpu().numpy()
+            if sha(got) != g["planes"][plano][mej]:
+                pytest.fail(explain(got, oracle_all(vxyz, plano, mej), f"noise {plano} {mej}"))
+            G = res[(mej, plano)][0].flip(-2).transpose(-1, -2).contiguous().cpu().numpy()
+            assert sha(G) == g["planes"][plano][mej], (plano, mej, "volume mode")
+
+
+@pytest.mark.parametrize("shape_xyz", [(37, 45, 29), (8, 8, 8), (64, 24, 16), (33, 18, 50)])
+def test_odd_shapes_vs_oracle(ops, torch_mod, cuda_device, shape_xyz):
+    torch = torch_mod
+    nv = _noise(100 + shape_xyz[0], shape_xyz)
+    vol = torch.from_numpy(nv).to(cuda_device)[None].contiguous()
+    vxyz = S.as_xyz(nv).astype(np.float64)
+    res = ops.enhance_volumes(vol)
+    for plano in PLANOS:
+        for mej in MEJORAS:
+            want = oracle_all(vxyz, plano, mej)
+            got = ops.enhance_slices(vol, mej, plano, layout="G").cpu().numpy()
+            assert np.array_equal(got, want), explain(got, want, f"{shape_xyz} {plano} {mej}")
+            G = res[(mej, plano)][0].flip(-2).transpose(-1, -2).contiguous().cpu().numpy()
+            assert np.array_equal(G, want), explain(G, want, f"{shape_xyz} {plano} {mej} volume mode")
+
+
+def test_slice_lists_layouts_and_png(ops, torch_mod, cuda_device):
+    torch = torch_mod
+    pats = [S.make_patient(n, config_id=1, with_predictions=False) for n in (8, 9)]
+    vol = torch.from_numpy(np.stack([p.flair for p in pats])).to(cuda_device)
+    gtd = torch.from_numpy(np.stack([p.gt for p in pats])).to(cuda_device)
+    rng = np.random.default_rng(0)
+    for plano in PLANOS:
+        n_p = S.SHAPE_XYZ[O.plane_axis(plano)]
+        vs = rng.integers(0, 2, 9).astype(np.int32)
+        ix = rng.integers(0, n_p, 9).astype(np.int32)
+        ix[0], ix[1] = 0, n_p - 1                      # blank border slices
+        for mej in MEJORAS:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                Gs = [O.enhance_slice(O.slice_of(S.as_xyz(pats[v].flair).astype(np.float64), plano, i), mej)
+                      for v, i in zip(vs, ix)]
+            got = ops.enhance_slices(vol, mej, plano, vs, ix, layout="G").cpu().numpy()
+            assert np.array_equal(got, np.stack(Gs)), (plano, mej, "G")
+            got = ops.enhance_slices(vol, mej, plano, vs, ix, layout="P").cpu().numpy()
+            assert np.array_equal(got, np.stack([O.png_orient(g) for g in Gs])), (plano, mej, "P")
+            got = ops.enhance_slices(vol, mej, plano, vs, ix, layout="PNG_GRAY").cpu().numpy()
+            assert np.array_equal(got, np.stack([O.imsave_gray(g) for g in Gs])), (plano, mej, "PNG_GRAY")
+            got = ops.enhance_slices(vol, mej, plano, vs, ix, layout="PNG_RGBA").cpu().numpy()
+            assert np.array_equal(got, np.stack([O.imsave_rgba(g) for g in Gs])), (plano, mej, "PNG_RGBA")
+        # mejora=None: imsave of the raw float64 slice (float64 normalisation)
+        raw = [O.slice_of(S.as_xyz(pats[v].flair).astype(np.float64), plano, i) for v, i in zip(vs, ix)]
+        got = ops.enhance_slices(vol, None, plano, vs, ix, layout="PNG_GRAY").cpu().numpy()
+        assert np.array_equal(got, np.stack([O.imsave_gray(r) for r in raw])), (plano, "None PNG_GRAY")
+        got = ops.enhance_slices(vol, None, plano, vs, ix, layout="PNG_RGBA").cpu().numpy()
+        assert np.array_equal(got, np.stack([O.imsave_rgba(r) for r in raw])), (plano, "None PNG_RGBA")
+        # ground-truth mask slices: raw gather and their imsave ({0,1} -> {0,255})
+        masks = [O.slice_of(S.as_xyz(pats[v].gt), plano, i) for v, i in zip(vs, ix)]
+        got = ops.enhance_slices(gtd, None, plano, vs, ix, layout="G").cpu().numpy()
+        assert np.array_equal(got, np.stack(masks)), (plano, "mask G")
+        got = ops.enhance_slices(gtd, None, plano, vs, ix, layout="PNG_GRAY").cpu().numpy()
+        assert np.array_equal(got, np.stack([O.imsave_gray(m.astype(np.float64)) for m in masks])), (plano, "mask PNG")
+
+
+def test_uint8_images_and_degenerate_inputs(ops, torch_mod, cuda_device):
+    torch = torch_mod
+    rng = np.random.default_rng(4)
+    imgs = np.stack([rng.integers(0, 256, (50, 70), dtype=np.uint8),
+                     (rng.integers(0, 5, (50, 70)) * 40).astype(np.uint8),     # max 160: LT table row != 255
+                     np.full((50, 70), 9, np.uint8), np.zeros((50, 70), np.uint8)])
+    d = torch.from_numpy(imgs).to(cuda_device)
+    for mej in MEJORAS:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = np.stack([O.enhance_u8(u, mej) for u in imgs])
+        got = ops.enhance_images(d, mej).cpu().numpy()
+        assert np.array_equal(got, want), mej
+    # blank float slices: HE 0, CLAHE 4, GC 0, LT 0
+    z = torch.zeros((1, 182, 218), dtype=torch.float32, device=cuda_device)
+    assert [int(ops.enhance_images(z, m).unique().item()) for m in MEJORAS] == [0, 4, 0, 0]
+    # empty slice list
+    vol = torch.zeros((1, 8, 8, 8), dtype=torch.float32, device=cuda_device)
+    assert ops.enhance_slices(vol, "GC", "axial", [], []).shape == (0, 8, 8)
+    # out-of-range entries are skipped (their output stays untouched)
+    out = torch.full((2, 8, 8), 7, dtype=torch.uint8, device=cuda_device)
+    ops.enhance_slices(vol, "GC", "axial", [0, 0], [3, 99], out=out)
+    assert int(out[0].max()) == 0 and int(out[1].min()) == 7
+
+
+def test_lesion_slices_golden(ops, torch_mod, golden, cuda_device):
+    torch = torch_mod
+    pats = [S.make_patient(n, config_id=1, num_cortes=20) for n in (1, 2)]
+    gt = torch.from_numpy(np.stack([p.gt for p in pats])).to(cuda_device)
+    flags = [f.cpu().numpy() for f in ops.lesion_slices(gt)]
+    flags_f32 = [f.cpu().numpy() for f in ops.lesion_slices(gt.float())]
+    for v, p in enumerate(pats):
+        for k, plano in enumerate(PLANOS):
+            pe = golden["synthetic_enhance"][p.id]["planes"][plano]
+            lesion = np.flatnonzero(flags[k][v]).astype(np.int32)
+            assert len(lesion) == pe["n_lesion"]
+            assert sha(lesion) == pe["lesion_sha"]
+            assert np.array_equal(flags[k][v], flags_f32[k][v])
+
+
+# ------------------------------------------------------------------------------ output side
+def test_recon_consensus_eval_golden(ops, torch_mod, golden, cuda_device):
+    torch = torch_mod
+    from mslesseg_b200 import metrics as M
+    ids = ["P54", "P55", "P56"]
+    pats = [S.make_patient(int(p[1:]), config_id=2, num_cortes=20) for p in ids]
+    gt = torch.from_numpy(np.stack([p.gt for p in pats])).to(cuda_device)
+    vols = {}
+    for plano in PLANOS:
+        sl = torch.from_numpy(np.concatenate([p.pred_slices[plano] for p in pats])).to(cuda_device)
+        vs = np.concatenate([np.full(len(p.pred_indices[plano]), v, np.int32) for v, p in enumerate(pats)])
+        ix = np.concatenate([np.asarray(p.pred_indices[plano], np.int32) for p in pats])
+        vols[plano] = ops.recon(sl, vs, ix, plano, len(pats), S.SHAPE_XYZ)
+        f32 = ops.recon(sl, vs, ix, plano, len(pats), S.SHAPE_XYZ, dtype=torch.float32)
+        for v, pid in enumerate(ids):
+            pe = golden["synthetic_eval"][pid]["planes"][plano]
+            assert sha(vols[plano][v].cpu().numpy()) == pe["recon_u8_sha"], (pid, plano)
+            assert sha(f32[v].cpu().numpy()) == pe["recon_f32_sha"], (pid, plano)
+    for umbral in (2, 3):
+        cons, counts = ops.consensus_eval(vols["axial"], vols["coronal"], vols["sagital"], gt, umbral)
+        counts = counts.cpu().numpy()
+        for v, pid in enumerate(ids):
+            ge = golden["synthetic_eval"][pid]
+            assert sha(cons[v].cpu().numpy()) == ge[f"consenso{umbral}"]["sha"]
+            for k, plano in enumerate(PLANOS):
+                assert counts[v, k].tolist() == ge["planes"][plano]["counts"]
+                assert M.metricas_desde_conteos(*counts[v, k]) == ge["planes"][plano]["metricas"]
+            assert counts[v, 3].tolist() == ge[f"consenso{umbral}"]["counts"]
+            assert M.metricas_desde_conteos(*counts[v, 3]) == ge[f"consenso{umbral}"]["metricas"]
+        # stand-alone count kernel == fused kernel
+        c1 = ops.confusion_counts(gt, cons).cpu().numpy()
+        assert np.array_equal(c1, counts[:, 3])
+    # vote only / counts only
+    cons_only, none = ops.consensus_eval(vols["axial"], vols["coronal"], vols["sagital"], None, 2)
+    assert none is None and torch.equal(cons_only, ops.consensus_eval(vols["axial"], vols["coronal"], vols["sagital"], gt, 2)[0])
+    no_cons, cnt = ops.consensus_eval(vols["axial"], vols["coronal"], vols["sagital"], gt, 2, want_consenso=False)
+    assert no_cons is None and cnt is not None
+
+
+def test_vote_and_counts_unaligned_and_nonbinary(ops, torch_mod, cuda_device):
+    torch = torch_mod
+    rng = np.random.default_rng(8)
+    for nvox, nvol in ((1003, 3), (64, 2), (7221032 // 182, 2)):
+        a, b, c, g = (rng.integers(0, 2, (nvol, nvox), dtype=np.uint8) for _ in range(4))
+        # sprinkle non-binary bytes: they must fall out of every ==0 / ==1 predicate like in the reference
+        a[:, ::37] = 5; g[:, ::53] = 2; b[:, 3::41] = 255
+        d = [torch.from_numpy(x).to(cuda_device) for x in (a, b, c, g)]
+        for umbral in (1, 2, 3, 4):
+            cons, counts = ops.consensus_eval(d[0], d[1], d[2], d[3], umbral)
+            want = O.combinar_volumenes(a.astype(np.float64), b.astype(np.float64), c.astype(np.float64), umbral)
+            assert np.array_equal(cons.cpu().numpy(), want), (nvox, umbral)
+            for v in range(nvol):
+                for k, p in enumerate((a, b, c, want)):
+                    assert counts[v, k].tolist() == list(O.confusion_counts(g[v], p[v])), (nvox, umbral, v, k)
+
+
+def test_recon_duplicates_sparse_and_empty(ops, torch_mod, cuda_device):
+    torch = torch_mod
+    X, Y, Z = 20, 14, 10
+    rng = np.random.default_rng(2)
+    for plano in PLANOS:
+        n_p, rows, cols = ops.plane_dims(plano, X, Y, Z)
+        idx = [1, n_p - 1, 3]
+        sl = (rng.random((3, rows, cols)) < 0.3).astype(np.uint8) * 255
+        sl[2] = (sl[2] > 0).astype(np.uint8)              # a {0,1}-valued mask is kept as is
+        want = O.reconstruir(list(sl), idx, (X, Y, Z), plano)
+        got = ops.recon(torch.from_numpy(sl).to(cuda_device), [0, 0, 0], idx, plano, 2, (X, Y, Z))
+        assert np.array_equal(got[0].cpu().numpy(), want.transpose(2, 1, 0).astype(np.uint8)), plano
+        assert int(got[1].sum()) == 0                      # second volume has no slices -> zeros
+        with pytest.raises(ValueError):
+            ops.recon(torch.zeros((1, rows + 1, cols), dtype=torch.uint8, device=cuda_device), [0], [0], plano, 1, (X, Y, Z))
+    empty = ops.recon(torch.zeros((0, X, Y), dtype=torch.uint8, device=cuda_device), [], [], "axial", 1, (X, Y, Z))
+    assert int(empty.sum()) == 0
+
+
+def test_no_cpu_fallback(ops, torch_mod):
+    torch = torch_mod
+    with pytest.raises(TypeError):
+        ops.enhance_images(torch.zeros((1, 8, 8)), "GC")

@@ -1,0 +1,267 @@
+// extern "C" entry points of libmslesseg.so (declared in include/mslesseg.h): argument validation,
+// geometry (plane -> strides, OpenCV's CLAHE tile geometry) and the launch sequences.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "msl_common.cuh"
+#include "msl_kernels.h"
+
+namespace msl {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+#define MSL_REQUIRE(cond, ...)                      \
+    do {                                            \
+        if (!(cond)) {                              \
+            msl::set_error(__VA_ARGS__);            \
+            return MSL_ERR_ARG;                     \
+        }                                           \
+    } while (0)
+
+inline int n_plane_of(int plano, int X, int Y, int Z) { return plano == MSL_AXIAL ? Z : (plano == MSL_CORONAL ? Y : X); }
+
+// OpenCV CLAHE_Impl::apply geometry for clipLimit 2.0 and an 8x8 grid (reference
+// utils/mejora_imagen.py:86,104).
+void clahe_geometry(int rows, int cols, EnhParams& p) {
+    int prow = rows, pcol = cols;
+    if (!(cols % 8 == 0 && rows % 8 == 0)) {
+        prow = rows + (8 - rows % 8);
+        pcol = cols + (8 - cols % 8);
+    }
+    p.cl_th = prow / 8;
+    p.cl_tw = pcol / 8;
+    const int area = p.cl_th * p.cl_tw;
+    int clip = (int)(2.0 * area / 256);
+    p.cl_clip = clip > 1 ? clip : 1;
+    p.cl_lut_scale = 255.0f / (float)area;
+}
+
+int check_enhance_combo(int mejora, int dtype, int layout) {
+    MSL_REQUIRE(mejora >= MSL_MEJORA_NONE && mejora <= MSL_MEJORA_LT, "mejora %d no reconocida", mejora);
+    MSL_REQUIRE(dtype == MSL_F32 || dtype == MSL_U8, "dtype %d not in {MSL_F32, MSL_U8}", dtype);
+    MSL_REQUIRE(layout >= MSL_OUT_G && layout <= MSL_OUT_PNG_RGBA, "layout %d not in MSL_OUT_*", layout);
+    if (mejora == MSL_MEJORA_NONE && dtype == MSL_F32 && layout < MSL_OUT_PNG_GRAY) {
+        set_error("mejora NONE on float input is only defined for the PNG layouts (the raw slice has no uint8 form)");
+        return MSL_ERR_UNSUPPORTED;
+    }
+    return MSL_OK;
+}
+
+int check_out(const uint8_t* out, size_t pitch, int npx, int layout) {
+    MSL_REQUIRE(out != nullptr, "out is NULL");
+    const size_t need = layout == MSL_OUT_PNG_RGBA ? (size_t)npx * 4 : (size_t)npx;
+    MSL_REQUIRE(pitch >= need, "output pitch %zu smaller than a slice (%zu bytes)", pitch, need);
+    if (layout == MSL_OUT_PNG_RGBA)
+        MSL_REQUIRE(pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0, "RGBA output must be 4-byte aligned");
+    return MSL_OK;
+}
+
+}  // namespace
+}  // namespace msl
+
+using namespace msl;
+
+extern "C" {
+
+int msl_version(void) { return MSL_ABI_VERSION; }
+
+const char* msl_last_error(void) { return g_err; }
+
+static int enhance_chunk_volumes(void) {
+    const char* e = getenv("MSL_VOLUME_CHUNK");
+    int c = e ? atoi(e) : 4;
+    return c < 1 ? 1 : c;
+}
+
+size_t msl_workspace_bytes(int op, int nvol, int X, int Y, int Z) {
+    if (nvol <= 0 || X <= 0 || Y <= 0 || Z <= 0) return 0;
+    const size_t N = (size_t)X * Y * Z;
+    switch (op) {
+        case MSL_WS_ENHANCE_VOLUMES: {
+            size_t stats = (((size_t)nvol * (X + Y + Z) * 2 * sizeof(unsigned)) + 255) & ~(size_t)255;
+            int chunk = enhance_chunk_volumes();
+            if (chunk > nvol) chunk = nvol;
+            return stats + 3 * (size_t)chunk * ((N + 255) & ~(size_t)255);
+        }
+        case MSL_WS_RECON: {
+            int m = X > Y ? X : Y;
+            if (Z > m) m = Z;
+            return (size_t)nvol * m * sizeof(int32_t);
+        }
+        default:
+            return 0;
+    }
+}
+
+int msl_lesion_slices(const void* gt, int dtype, int nvol, int X, int Y, int Z,
+                      uint8_t* any_ax, uint8_t* any_co, uint8_t* any_sa, msl_stream_t stream) {
+    MSL_REQUIRE(gt && any_ax && any_co && any_sa, "NULL pointer");
+    MSL_REQUIRE(dtype == MSL_F32 || dtype == MSL_U8, "dtype %d not in {MSL_F32, MSL_U8}", dtype);
+    MSL_REQUIRE(nvol > 0 && X > 0 && Y > 0 && Z > 0, "non-positive size");
+    MSL_REQUIRE(nvol <= 65535, "at most 65535 volumes per call");
+    return launch_lesion_flags(gt, dtype, nvol, X, Y, Z, any_ax, any_co, any_sa, (cudaStream_t)stream);
+}
+
+int msl_enhance_slices(const void* vol, int dtype, int nvol, int X, int Y, int Z, int mejora, int plano,
+                       const int32_t* vol_of_slice, const int32_t* idx_of_slice, int nslices,
+                       uint8_t* out, size_t slice_pitch_bytes, int layout, const uint8_t* tables, msl_stream_t stream) {
+    MSL_REQUIRE(vol && tables, "NULL pointer");
+    MSL_REQUIRE(nvol > 0 && X > 0 && Y > 0 && Z > 0 && nslices >= 0, "non-positive size");
+    MSL_REQUIRE(plano >= MSL_AXIAL && plano <= MSL_SAGITAL, "Plano %d no válido.", plano);
+    int rc = check_enhance_combo(mejora, dtype, layout);
+    if (rc) return rc;
+    MSL_REQUIRE((vol_of_slice == nullptr) == (idx_of_slice == nullptr), "vol_of_slice and idx_of_slice must both be given or both be NULL");
+    EnhParams p;
+    memset(&p, 0, sizeof(p));
+    const long long N = (long long)X * Y * Z;
+    p.in = vol;
+    p.vol_stride = N;
+    p.nvol = nvol;
+    p.n_plane = n_plane_of(plano, X, Y, Z);
+    if (plano == MSL_AXIAL) { p.rows = X; p.cols = Y; p.sa = 1; p.sb = X; p.idx_stride = (long long)X * Y; }
+    else if (plano == MSL_CORONAL) { p.rows = X; p.cols = Z; p.sa = 1; p.sb = (long long)X * Y; p.idx_stride = X; }
+    else { p.rows = Y; p.cols = Z; p.sa = X; p.sb = (long long)X * Y; p.idx_stride = 1; }
+    if (!vol_of_slice)
+        MSL_REQUIRE((long long)nslices == (long long)nvol * p.n_plane, "dense mode needs nslices == nvol * n_plane (%lld), got %d",
+                    (long long)nvol * p.n_plane, nslices);
+    if (nslices == 0) return MSL_OK;
+    rc = check_out(out, slice_pitch_bytes, p.rows * p.cols, layout);
+    if (rc) return rc;
+    p.vol_of_slice = vol_of_slice; p.idx_of_slice = idx_of_slice;
+    p.out = out; p.out_pitch = slice_pitch_bytes; p.layout = layout; p.mejora = mejora; p.tables = tables;
+    clahe_geometry(p.rows, p.cols, p);
+    return launch_enhance_slices(p, dtype, nslices, (cudaStream_t)stream);
+}
+
+int msl_enhance_images(const void* imgs, int dtype, int nimg, int rows, int cols, size_t img_pitch_elems,
+                       int mejora, uint8_t* out, size_t out_pitch_bytes, int layout, const uint8_t* tables, msl_stream_t stream) {
+    MSL_REQUIRE(imgs && tables, "NULL pointer");
+    MSL_REQUIRE(nimg >= 0 && rows > 0 && cols > 0, "non-positive size");
+    MSL_REQUIRE(img_pitch_elems >= (size_t)rows * cols, "image pitch smaller than an image");
+    int rc = check_enhance_combo(mejora, dtype, layout);
+    if (rc) return rc;
+    if (nimg == 0) return MSL_OK;
+    rc = check_out(out, out_pitch_bytes, rows * cols, layout);
+    if (rc) return rc;
+    EnhParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = imgs; p.vol_stride = (long long)img_pitch_elems; p.idx_stride = 0; p.base0 = 0;
+    p.sa = cols; p.sb = 1; p.rows = rows; p.cols = cols; p.nvol = nimg; p.n_plane = 1;
+    p.out = out; p.out_pitch = out_pitch_bytes; p.layout = layout; p.mejora = mejora; p.tables = tables;
+    clahe_geometry(rows, cols, p);
+    return launch_enhance_slices(p, dtype, nimg, (cudaStream_t)stream);
+}
+
+int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z, uint8_t* const* outs, const uint8_t* tables,
+                        void* ws, size_t ws_bytes, msl_stream_t stream_) {
+    MSL_REQUIRE(vol && outs && tables, "NULL pointer");
+    MSL_REQUIRE(nvol > 0 && X > 0 && Y > 0 && Z > 0, "non-positive size");
+    MSL_REQUIRE(nvol <= 65535, "at most 65535 volumes per call");
+    if (X > 256) { set_error("msl_enhance_volumes supports X <= 256 (got %d)", X); return MSL_ERR_UNSUPPORTED; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t need = msl_workspace_bytes(MSL_WS_ENHANCE_VOLUMES, nvol, X, Y, Z);
+    if (!ws || ws_bytes < need) { set_error("workspace of %zu bytes needed, %zu given", need, ws_bytes); return MSL_ERR_WORKSPACE; }
+    bool any = false, need_u = false;
+    for (int k = 0; k < 12; ++k) any |= outs[k] != nullptr;
+    for (int k = 0; k < 6; ++k) need_u |= outs[k] != nullptr;     // HE (0-2) and CLAHE (3-5) consume the normalised stacks
+    if (!any) return MSL_OK;
+
+    const size_t N = (size_t)X * Y * Z;
+    const size_t nsl = (size_t)nvol * (X + Y + Z);
+    unsigned* stats = reinterpret_cast<unsigned*>(ws);
+    const size_t stats_bytes = ((nsl * 2 * sizeof(unsigned)) + 255) & ~(size_t)255;
+    const size_t ustride = (N + 255) & ~(size_t)255;
+    int chunk = enhance_chunk_volumes();
+    if (chunk > nvol) chunk = nvol;
+    uint8_t* ubase = reinterpret_cast<uint8_t*>(ws) + stats_bytes;
+    uint8_t* U[3] = {ubase, ubase + (size_t)chunk * ustride, ubase + 2 * (size_t)chunk * ustride};
+    // NB: the three U stacks are densely packed per chunk: [chunk][n_p][cols][rows] = chunk * N bytes each.
+
+    int rc = launch_init_stats(stats, nsl, stream);
+    if (rc) return rc;
+    const int n_p[3] = {Z, Y, X};
+    const int rows_p[3] = {X, X, Y}, cols_p[3] = {Y, Z, Z};
+    for (int v0 = 0; v0 < nvol; v0 += chunk) {
+        const int nv = (nvol - v0) < chunk ? (nvol - v0) : chunk;
+        const float* cvol = vol + (size_t)v0 * N;
+        unsigned* cstats = stats + (size_t)v0 * (X + Y + Z) * 2;
+        rc = launch_plane_stats_f32(cvol, nv, X, Y, Z, cstats, stream);
+        if (rc) return rc;
+        ScatterOuts so;
+        memset(&so, 0, sizeof(so));
+        for (int pl = 0; pl < 3; ++pl) {
+            if (need_u) so.o[0][pl] = U[pl];
+            if (outs[(MSL_MEJORA_GC - 1) * 3 + pl]) so.o[1][pl] = outs[(MSL_MEJORA_GC - 1) * 3 + pl] + (size_t)v0 * N;
+            if (outs[(MSL_MEJORA_LT - 1) * 3 + pl]) so.o[2][pl] = outs[(MSL_MEJORA_LT - 1) * 3 + pl] + (size_t)v0 * N;
+        }
+        // only stage the normalised plane stacks that HE / CLAHE will actually read
+        for (int pl = 0; pl < 3; ++pl)
+            if (!outs[(MSL_MEJORA_HE - 1) * 3 + pl] && !outs[(MSL_MEJORA_CLAHE - 1) * 3 + pl]) so.o[0][pl] = nullptr;
+        rc = launch_norm_scatter(cvol, nv, X, Y, Z, cstats, so, tables, stream);
+        if (rc) return rc;
+        for (int mej = MSL_MEJORA_HE; mej <= MSL_MEJORA_CLAHE; ++mej) {
+            for (int pl = 0; pl < 3; ++pl) {
+                uint8_t* dst = outs[(mej - 1) * 3 + pl];
+                if (!dst) continue;
+                // the staged stack is in PNG orientation: G[a, b] = P[cols-1-b, a]
+                EnhParams p;
+                memset(&p, 0, sizeof(p));
+                const int rows = rows_p[pl], cols = cols_p[pl], npx = rows * cols;
+                p.in = U[pl];
+                p.vol_stride = (long long)n_p[pl] * npx; p.idx_stride = npx; p.base0 = (long long)(cols - 1) * rows;
+                p.sa = 1; p.sb = -(long long)rows; p.rows = rows; p.cols = cols; p.nvol = nv; p.n_plane = n_p[pl];
+                p.out = dst + (size_t)v0 * N; p.out_pitch = npx; p.layout = MSL_OUT_P; p.mejora = mej; p.tables = tables;
+                clahe_geometry(rows, cols, p);
+                rc = launch_enhance_slices(p, MSL_U8, nv * n_p[pl], stream);
+                if (rc) return rc;
+            }
+        }
+    }
+    return MSL_OK;
+}
+
+int msl_recon(const uint8_t* slices, size_t slice_pitch_bytes, const int32_t* vol_of_slice, const int32_t* idx_of_slice,
+              int nslices, int plano, int nvol, int X, int Y, int Z, uint8_t* vol_u8, float* vol_f32,
+              void* ws, size_t ws_bytes, msl_stream_t stream) {
+    MSL_REQUIRE(nvol > 0 && X > 0 && Y > 0 && Z > 0 && nslices >= 0, "non-positive size");
+    MSL_REQUIRE(nvol <= 65535, "at most 65535 volumes per call");
+    MSL_REQUIRE(plano >= MSL_AXIAL && plano <= MSL_SAGITAL, "Plano %d no válido.", plano);
+    MSL_REQUIRE(vol_u8 || vol_f32, "one of vol_u8 / vol_f32 must be given");
+    MSL_REQUIRE(nslices == 0 || (slices && vol_of_slice && idx_of_slice), "NULL slice arrays");
+    const int rows = plano == MSL_SAGITAL ? Y : X, cols = plano == MSL_AXIAL ? Y : Z;
+    MSL_REQUIRE(nslices == 0 || slice_pitch_bytes >= (size_t)rows * cols, "slice pitch smaller than a %d x %d slice", rows, cols);
+    const size_t need = msl_workspace_bytes(MSL_WS_RECON, nvol, X, Y, Z);
+    if (!ws || ws_bytes < need) { set_error("workspace of %zu bytes needed, %zu given", need, ws_bytes); return MSL_ERR_WORKSPACE; }
+    return launch_recon(slices, slice_pitch_bytes, vol_of_slice, idx_of_slice, nslices, plano, nvol, X, Y, Z,
+                        vol_u8, vol_f32, reinterpret_cast<int32_t*>(ws), (cudaStream_t)stream);
+}
+
+int msl_consensus_eval(const uint8_t* ax, const uint8_t* co, const uint8_t* sa, const uint8_t* gt, int nvol, size_t nvox,
+                       int umbral, uint8_t* consenso, int64_t* counts, msl_stream_t stream) {
+    MSL_REQUIRE(ax && co && sa, "NULL plane volume");
+    MSL_REQUIRE((gt == nullptr) == (counts == nullptr), "gt and counts must both be given or both be NULL");
+    MSL_REQUIRE(gt || consenso, "nothing to compute: neither consenso nor counts requested");
+    MSL_REQUIRE(nvol > 0 && nvox > 0, "non-positive size");
+    MSL_REQUIRE(nvol <= 65535, "at most 65535 volumes per call");
+    return launch_consensus_eval(ax, co, sa, gt, nvol, nvox, umbral, consenso, reinterpret_cast<long long*>(counts),
+                                 (cudaStream_t)stream);
+}
+
+int msl_confusion_counts(const uint8_t* gt, const uint8_t* pred, int nvol, size_t nvox, int64_t* counts, msl_stream_t stream) {
+    MSL_REQUIRE(gt && pred && counts, "NULL pointer");
+    MSL_REQUIRE(nvol > 0 && nvox > 0, "non-positive size");
+    MSL_REQUIRE(nvol <= 65535, "at most 65535 volumes per call");
+    return launch_confusion_counts(gt, pred, nvol, nvox, reinterpret_cast<long long*>(counts), (cudaStream_t)stream);
+}
+
+}  // extern "C"

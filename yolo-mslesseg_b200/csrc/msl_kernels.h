@@ -1,0 +1,64 @@
+// Internal launcher interface between the C ABI (msl_abi.cu) and the kernel translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace msl {
+
+// One launch of the slice-mode enhancement kernel: `nslices` CTAs, one slice each.
+struct EnhParams {
+    const void* in;              // element type given by the launcher's dtype
+    long long vol_stride;        // elements between volumes / images
+    long long idx_stride;        // elements between consecutive slice indices of the plane
+    long long base0;             // extra element offset (negative-stride views)
+    long long sa, sb;            // element strides of slice coordinates (a = row, b = col)
+    int rows, cols;              // slice shape in slice orientation
+    int nvol, n_plane;           // bounds for (vol_of_slice, idx_of_slice)
+    const int32_t* vol_of_slice; // device, or NULL for dense (s = v * n_plane + i)
+    const int32_t* idx_of_slice;
+    uint8_t* out;
+    size_t out_pitch;            // bytes between output slices
+    int layout;                  // MSL_OUT_*
+    int mejora;                  // MSL_MEJORA_*
+    const uint8_t* tables;       // MSL_TABLES_BYTES device bytes
+    // CLAHE geometry (host-computed exactly like OpenCV's CLAHE_Impl::apply)
+    int cl_th, cl_tw, cl_clip;
+    float cl_lut_scale;
+    int hist_bytes;              // filled by the launcher
+};
+
+size_t enhance_slices_smem_bytes(int mejora, int npx);
+int launch_enhance_slices(EnhParams p, int dtype, int nslices, cudaStream_t stream);
+
+// Tri-planar per-slice min/max of float volumes (keys are order-preserving uint32, see f2key).
+// stats: [nvol][Z + Y + X][2] = {min key, max key}; must be pre-initialised by init_stats.
+int launch_init_stats(unsigned* stats, size_t nslices_total, cudaStream_t stream);
+int launch_plane_stats_f32(const float* vol, int nvol, int X, int Y, int Z, unsigned* stats, cudaStream_t stream);
+
+// E0: any(voxel > 0) per slice for the three planes.
+int launch_lesion_flags(const void* gt, int dtype, int nvol, int X, int Y, int Z,
+                        uint8_t* any_ax, uint8_t* any_co, uint8_t* any_sa, cudaStream_t stream);
+
+// Normalise each voxel with the (min, ptp) of the three slices it belongs to and scatter the bytes
+// into three PNG-oriented slice stacks; up to three point-wise tables per voxel (identity/GC/LT).
+struct ScatterOuts {
+    // per variant (0 = normalised u, 1 = GC, 2 = LT) and plane; NULL = skip
+    uint8_t* o[3][3];
+};
+int launch_norm_scatter(const float* vol, int nvol, int X, int Y, int Z, const unsigned* stats,
+                        const ScatterOuts& outs, const uint8_t* tables, cudaStream_t stream);
+
+// R1-R2
+int launch_recon(const uint8_t* slices, size_t slice_pitch, const int32_t* vol_of_slice, const int32_t* idx_of_slice,
+                 int nslices, int plano, int nvol, int X, int Y, int Z, uint8_t* vol_u8, float* vol_f32,
+                 int32_t* slot_of, cudaStream_t stream);
+
+// R3-R4
+int launch_consensus_eval(const uint8_t* ax, const uint8_t* co, const uint8_t* sa, const uint8_t* gt,
+                          int nvol, size_t nvox, int umbral, uint8_t* consenso, long long* counts, cudaStream_t stream);
+int launch_confusion_counts(const uint8_t* gt, const uint8_t* pred, int nvol, size_t nvox, long long* counts,
+                            cudaStream_t stream);
+
+}  // namespace msl

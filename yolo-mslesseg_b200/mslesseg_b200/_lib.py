@@ -1,0 +1,77 @@
+"""ctypes binding of libmslesseg.so (C ABI declared in include/mslesseg.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails the
+caller gets an exception - the product path never routes through NumPy/PyTorch arithmetic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("MSLESSEG_LIB", _HERE / "libmslesseg.so"))
+
+# enums of include/mslesseg.h
+AXIAL, CORONAL, SAGITAL = 0, 1, 2
+MEJORA_NONE, MEJORA_HE, MEJORA_CLAHE, MEJORA_GC, MEJORA_LT = 0, 1, 2, 3, 4
+F32, U8 = 0, 1
+OUT_G, OUT_P, OUT_PNG_GRAY, OUT_PNG_RGBA = 0, 1, 2, 3
+WS_ENHANCE_VOLUMES, WS_RECON = 1, 2
+OK, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4
+
+PLANO_ID = {"axial": AXIAL, "coronal": CORONAL, "sagital": SAGITAL}
+MEJORA_ID = {None: MEJORA_NONE, "HE": MEJORA_HE, "CLAHE": MEJORA_CLAHE, "GC": MEJORA_GC, "LT": MEJORA_LT}
+
+
+class MslError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libmslesseg error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+_vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
+
+_SIGNATURES = {
+    "msl_version": (C.c_int, []),
+    "msl_last_error": (C.c_char_p, []),
+    "msl_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i, _i]),
+    "msl_lesion_slices": (C.c_int, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "msl_enhance_slices": (C.c_int, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _sz, _i, _vp, _vp]),
+    "msl_enhance_images": (C.c_int, [_vp, _i, _i, _i, _i, _sz, _i, _vp, _sz, _i, _vp, _vp]),
+    "msl_enhance_volumes": (C.c_int, [_vp, _i, _i, _i, _i, C.POINTER(C.c_void_p), _vp, _vp, _sz, _vp]),
+    "msl_recon": (C.c_int, [_vp, _sz, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "msl_consensus_eval": (C.c_int, [_vp, _vp, _vp, _vp, _i, _sz, _i, _vp, _vp, _vp]),
+    "msl_confusion_counts": (C.c_int, [_vp, _vp, _i, _sz, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads libmslesseg.so once; raises if it has not been built (see __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise FileNotFoundError(
+            f"{LIB_PATH} not found - build it with `make -C yolo-mslesseg_b200/csrc` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        msg = load().msl_last_error()
+        raise MslError(rc, msg.decode("utf-8", "replace") if msg else "")

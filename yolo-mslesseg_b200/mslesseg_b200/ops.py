@@ -1,0 +1,258 @@
+"""Batched device-tensor API over the C ABI (include/mslesseg.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every arithmetic step runs in
+the hand-written sm_100a kernels of libmslesseg.so.  All functions enqueue on
+`torch.cuda.current_stream()` and return device tensors without synchronising.
+
+Layouts: volumes are [nvol][Z][Y][X] (x fastest) - the same bytes as the reference's
+Fortran-ordered (X, Y, Z) arrays.  Slice stacks are [n][rows][cols] in slice orientation
+("G") or [n][cols][rows] in PNG orientation ("P", P[r, c] = G[c, cols-1-r]).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import tables as T
+
+PLANOS = ("axial", "coronal", "sagital")
+MEJORAS = ("HE", "CLAHE", "GC", "LT")
+_LAYOUT_ID = {"G": L.OUT_G, "P": L.OUT_P, "PNG_GRAY": L.OUT_PNG_GRAY, "PNG_RGBA": L.OUT_PNG_RGBA}
+_tables_cache: Dict[int, torch.Tensor] = {}
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need_cuda(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def _dtype_id(t: torch.Tensor, name: str) -> int:
+    if t.dtype == torch.float32:
+        return L.F32
+    if t.dtype == torch.uint8:
+        return L.U8
+    raise TypeError(f"{name} must be float32 or uint8, got {t.dtype}")
+
+
+def device_tables(device) -> torch.Tensor:
+    """The MSL_TABLES_BYTES constant block, uploaded once per device."""
+    dev = torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    t = _tables_cache.get(key)
+    if t is None:
+        t = torch.from_numpy(T.host_tables().copy()).to(dev)
+        _tables_cache[key] = t
+    return t
+
+
+def plane_dims(plano: str, X: int, Y: int, Z: int) -> Tuple[int, int, int]:
+    """(n_slices, rows, cols) of a plane (reference utils/Paciente.py:186-193, :240-244)."""
+    if plano == "axial":
+        return Z, X, Y
+    if plano == "coronal":
+        return Y, X, Z
+    if plano == "sagital":
+        return X, Y, Z
+    raise ValueError(f"Plano {plano} no válido.")
+
+
+def _index_tensor(a, device) -> torch.Tensor:
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=torch.int32).contiguous()
+    return torch.as_tensor(np.asarray(a, dtype=np.int32), device=device)
+
+
+def _out_shape(n: int, rows: int, cols: int, layout: str):
+    if layout == "G":
+        return (n, rows, cols)
+    if layout in ("P", "PNG_GRAY"):
+        return (n, cols, rows)
+    if layout == "PNG_RGBA":
+        return (n, cols, rows, 4)
+    raise ValueError(f"layout {layout!r} not in {sorted(_LAYOUT_ID)}")
+
+
+# ------------------------------------------------------------------------------------ E0
+def lesion_slices(gt: torch.Tensor):
+    """any(mask_slice > 0) for every slice of the three planes.  gt: [nvol, Z, Y, X] uint8/float32.
+    Returns (any_ax [nvol, Z], any_co [nvol, Y], any_sa [nvol, X]) uint8."""
+    _need_cuda(gt, "gt")
+    if gt.dim() != 4:
+        raise ValueError("gt must be [nvol, Z, Y, X]")
+    nvol, Z, Y, X = gt.shape
+    ax = torch.empty((nvol, Z), dtype=torch.uint8, device=gt.device)
+    co = torch.empty((nvol, Y), dtype=torch.uint8, device=gt.device)
+    sa = torch.empty((nvol, X), dtype=torch.uint8, device=gt.device)
+    L.check(L.load().msl_lesion_slices(_ptr(gt), _dtype_id(gt, "gt"), nvol, X, Y, Z, _ptr(ax), _ptr(co), _ptr(sa), _stream()))
+    return ax, co, sa
+
+
+# ------------------------------------------------------------------------------------ E1-E8
+def enhance_slices(vol: torch.Tensor, mejora: Optional[str], plano: str, vol_of_slice=None, idx_of_slice=None,
+                   layout: str = "G", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Enhanced slices of resident volumes.  vol: [nvol, Z, Y, X] float32 (normalised per slice like
+    normalizar_a_uint8) or uint8 (used as is).  With no index lists every slice of every volume is
+    produced (s = v * n_plane + i)."""
+    _need_cuda(vol, "vol")
+    if vol.dim() != 4:
+        raise ValueError("vol must be [nvol, Z, Y, X]")
+    if mejora not in L.MEJORA_ID:
+        raise ValueError(f"Mejora no reconocida: {mejora}.")
+    nvol, Z, Y, X = vol.shape
+    n_p, rows, cols = plane_dims(plano, X, Y, Z)
+    if (vol_of_slice is None) != (idx_of_slice is None):
+        raise ValueError("vol_of_slice and idx_of_slice go together")
+    if vol_of_slice is None:
+        ns, vs, ix = nvol * n_p, None, None
+    else:
+        vs, ix = _index_tensor(vol_of_slice, vol.device), _index_tensor(idx_of_slice, vol.device)
+        if vs.shape != ix.shape or vs.dim() != 1:
+            raise ValueError("vol_of_slice / idx_of_slice must be 1-D and of equal length")
+        ns = int(vs.numel())
+    shape = _out_shape(ns, rows, cols, layout)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.uint8, device=vol.device)
+    else:
+        _need_cuda(out, "out")
+        if tuple(out.shape) != shape or out.dtype != torch.uint8:
+            raise ValueError(f"out must be uint8 {shape}")
+    pitch = rows * cols * (4 if layout == "PNG_RGBA" else 1)
+    L.check(L.load().msl_enhance_slices(
+        _ptr(vol), _dtype_id(vol, "vol"), nvol, X, Y, Z, L.MEJORA_ID[mejora], L.PLANO_ID[plano],
+        _ptr(vs), _ptr(ix), ns, _ptr(out), pitch, _LAYOUT_ID[layout], _ptr(device_tables(vol.device)), _stream()))
+    return out
+
+
+def enhance_images(imgs: torch.Tensor, mejora: Optional[str], layout: str = "G") -> torch.Tensor:
+    """Batch of C-contiguous 2-D images [n, rows, cols] (float32 or uint8) -> enhanced gray images."""
+    _need_cuda(imgs, "imgs")
+    if imgs.dim() != 3:
+        raise ValueError("imgs must be [n, rows, cols]")
+    if mejora not in L.MEJORA_ID:
+        raise ValueError(f"Mejora no reconocida: {mejora}.")
+    n, rows, cols = imgs.shape
+    out = torch.empty(_out_shape(n, rows, cols, layout), dtype=torch.uint8, device=imgs.device)
+    pitch = rows * cols * (4 if layout == "PNG_RGBA" else 1)
+    L.check(L.load().msl_enhance_images(
+        _ptr(imgs), _dtype_id(imgs, "imgs"), n, rows, cols, rows * cols, L.MEJORA_ID[mejora],
+        _ptr(out), pitch, _LAYOUT_ID[layout], _ptr(device_tables(imgs.device)), _stream()))
+    return out
+
+
+def enhance_volumes_workspace_bytes(nvol: int, X: int, Y: int, Z: int) -> int:
+    return int(L.load().msl_workspace_bytes(L.WS_ENHANCE_VOLUMES, nvol, X, Y, Z))
+
+
+def enhance_volumes(vol: torch.Tensor, mejoras: Iterable[str] = MEJORAS, planos: Iterable[str] = PLANOS,
+                    outs: Optional[Dict[Tuple[str, str], torch.Tensor]] = None,
+                    workspace: Optional[torch.Tensor] = None) -> Dict[Tuple[str, str], torch.Tensor]:
+    """All slices of the requested planes and enhancements from ONE resident float32 copy.
+    Returns {(mejora, plano): uint8 [nvol, n_plane, cols, rows]} in PNG orientation; the slice-oriented
+    view is `P.flip(-2).transpose(-1, -2)`."""
+    _need_cuda(vol, "vol")
+    if vol.dim() != 4 or vol.dtype != torch.float32:
+        raise ValueError("vol must be float32 [nvol, Z, Y, X]")
+    nvol, Z, Y, X = vol.shape
+    mejoras, planos = tuple(mejoras), tuple(planos)
+    result: Dict[Tuple[str, str], torch.Tensor] = {}
+    ptrs = (C.c_void_p * 12)()
+    for m in mejoras:
+        if m not in MEJORAS:
+            raise ValueError(f"Mejora no reconocida: {m}.")
+        for pl in planos:
+            n_p, rows, cols = plane_dims(pl, X, Y, Z)
+            shape = (nvol, n_p, cols, rows)
+            t = None if outs is None else outs.get((m, pl))
+            if t is None:
+                t = torch.empty(shape, dtype=torch.uint8, device=vol.device)
+            else:
+                _need_cuda(t, f"outs[{m},{pl}]")
+                if tuple(t.shape) != shape or t.dtype != torch.uint8:
+                    raise ValueError(f"outs[{m},{pl}] must be uint8 {shape}")
+            result[(m, pl)] = t
+            ptrs[(L.MEJORA_ID[m] - 1) * 3 + L.PLANO_ID[pl]] = t.data_ptr()
+    need = enhance_volumes_workspace_bytes(nvol, X, Y, Z)
+    if workspace is None:
+        workspace = torch.empty(need, dtype=torch.uint8, device=vol.device)
+    _need_cuda(workspace, "workspace")
+    L.check(L.load().msl_enhance_volumes(_ptr(vol), nvol, X, Y, Z, ptrs, _ptr(device_tables(vol.device)),
+                                         _ptr(workspace), workspace.numel() * workspace.element_size(), _stream()))
+    return result
+
+
+# ------------------------------------------------------------------------------------ R1-R2
+def recon(slices: torch.Tensor, vol_of_slice, idx_of_slice, plano: str, nvol: int, shape_xyz: Sequence[int],
+          dtype: torch.dtype = torch.uint8, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Predicted masks [n, rows, cols] uint8 (pixel > 0 = lesion) -> volumes [nvol, Z, Y, X] of 0/1."""
+    X, Y, Z = (int(d) for d in shape_xyz)
+    n_p, rows, cols = plane_dims(plano, X, Y, Z)
+    _need_cuda(slices, "slices")
+    if slices.dtype != torch.uint8 or slices.dim() != 3 or tuple(slices.shape[1:]) != (rows, cols):
+        raise ValueError(
+            f"Dimensiones {tuple(slices.shape[1:])} incorrectas para plano {plano}. Se esperaba {(rows, cols)}.")
+    dev = slices.device
+    vs, ix = _index_tensor(vol_of_slice, dev), _index_tensor(idx_of_slice, dev)
+    ns = int(slices.shape[0])
+    if vs.numel() != ns or ix.numel() != ns:
+        raise ValueError("one (volume, index) pair per slice is required")
+    if dtype not in (torch.uint8, torch.float32):
+        raise TypeError("dtype must be torch.uint8 or torch.float32")
+    if out is None:
+        out = torch.empty((nvol, Z, Y, X), dtype=dtype, device=dev)
+    ws_bytes = int(L.load().msl_workspace_bytes(L.WS_RECON, nvol, X, Y, Z))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    u8 = out if out.dtype == torch.uint8 else None
+    f32 = out if out.dtype == torch.float32 else None
+    L.check(L.load().msl_recon(_ptr(slices), rows * cols, _ptr(vs), _ptr(ix), ns, L.PLANO_ID[plano], nvol, X, Y, Z,
+                               _ptr(u8), _ptr(f32), _ptr(ws), ws_bytes, _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------ R3-R4
+def consensus_eval(ax: torch.Tensor, co: torch.Tensor, sa: torch.Tensor, gt: Optional[torch.Tensor] = None,
+                   umbral: int = 2, want_consenso: bool = True):
+    """(ax + co + sa >= umbral) and, when gt is given, int64 counts [nvol, 4 planes, (tp, fp, fn, tn)]
+    for axial, coronal, sagital and consenso in the same pass.  Returns (consenso | None, counts | None)."""
+    for name, t in (("ax", ax), ("co", co), ("sa", sa)):
+        _need_cuda(t, name)
+        if t.dtype != torch.uint8 or t.shape != ax.shape:
+            raise ValueError("ax / co / sa must be uint8 tensors of one shape")
+    nvol = ax.shape[0] if ax.dim() > 1 else 1
+    nvox = ax.numel() // nvol
+    counts = None
+    if gt is not None:
+        _need_cuda(gt, "gt")
+        if gt.dtype != torch.uint8 or gt.shape != ax.shape:
+            raise ValueError("gt must be a uint8 tensor shaped like the plane volumes")
+        counts = torch.empty((nvol, 4, 4), dtype=torch.int64, device=ax.device)
+    cons = torch.empty_like(ax) if want_consenso else None
+    L.check(L.load().msl_consensus_eval(_ptr(ax), _ptr(co), _ptr(sa), _ptr(gt), nvol, nvox, int(umbral),
+                                        _ptr(cons), _ptr(counts), _stream()))
+    return cons, counts
+
+
+def confusion_counts(gt: torch.Tensor, pred: torch.Tensor) -> torch.Tensor:
+    """int64 [nvol, (tp, fp, fn, tn)] with the reference's exact ==1 / ==0 predicates."""
+    _need_cuda(gt, "gt")
+    _need_cuda(pred, "pred")
+    if gt.dtype != torch.uint8 or pred.dtype != torch.uint8 or gt.shape != pred.shape:
+        raise ValueError("gt and pred must be uint8 tensors of one shape")
+    nvol = gt.shape[0] if gt.dim() > 1 else 1
+    nvox = gt.numel() // nvol
+    counts = torch.empty((nvol, 4), dtype=torch.int64, device=gt.device)
+    L.check(L.load().msl_confusion_counts(_ptr(gt), _ptr(pred), nvol, nvox, _ptr(counts), _stream()))
+    return counts
