@@ -130,6 +130,8 @@ def enhance_slices(vol: torch.Tensor, mejora: Optional[str], plano: str, vol_of_
         _need_cuda(out, "out")
         if tuple(out.shape) != shape or out.dtype != torch.uint8:
             raise ValueError(f"out must be uint8 {shape}")
+    if ns == 0:                      # an empty tensor has a NULL data pointer, which the ABI reads as "dense"
+        return out
     pitch = rows * cols * (4 if layout == "PNG_RGBA" else 1)
     L.check(L.load().msl_enhance_slices(
         _ptr(vol), _dtype_id(vol, "vol"), nvol, X, Y, Z, L.MEJORA_ID[mejora], L.PLANO_ID[plano],
