@@ -1,0 +1,481 @@
+#!/usr/bin/env python
+"""bench.py - throughput of the YOLO-MSLesSeg voxel path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (port), host cores
+
+One STEP = one pass of the hot path over one batch of synthetic patients resident in HBM:
+  enhance->slice : lesion-slice flags (E0) + HE / CLAHE / GC / LT x axial / coronal / sagital over ALL
+                   slices of every volume (E1-E7, msl_enhance_volumes: 12 PNG-oriented uint8 stacks)
+  recon->consensus->eval : stack the predicted masks of the three planes into volumes (R1-R2), tri-planar
+                   vote fused with the 4x4 confusion counts (R3-R4); at N > 1 the int64 count table is
+                   all-reduced over NCCL; the float64 metric formulas run on the host outside the step.
+This is configs[1] of BASELINE.json ("single synthetic patient, all four enhancements + tri-planar
+slicing") batched over `--batch` distinct patients per GPU so that the inputs (batch x 28.9 MB) exceed
+the 126 MB L2 - no L2 flush is needed between iterations - followed by the output side of configs[2].
+
+`value` = patients x 7,221,032 voxels / step time (data resident in HBM, CUDA events, max over ranks).
+`e2e`   = same metric through the public API with pinned HOST buffers: H2D of the volumes / masks /
+          predicted slices and D2H of every result (12 stacks, 3 recon volumes, consensus, counts)
+          inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for _p in (str(ROOT), str(ROOT / "yolo-mslesseg_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+N_VOX = 182 * 218 * 182
+METRIC = "Gvoxel/s enhance->slice (HE/CLAHE/GC/LT x 3 planes) + recon->consensus->eval"
+UNIT = "Gvoxel/s"
+PLANOS = ("axial", "coronal", "sagital")
+MEJORAS = ("HE", "CLAHE", "GC", "LT")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="synthetic patients per GPU per step")
+    ap.add_argument("--num-cortes", type=int, default=40, help="predicted slices kept per plane (indices_a_usar)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, extra=None):
+    cfg = {
+        "workload": (f"configs[1] batched: {args.batch} synthetic 182x218x182 patients per GPU per step, "
+                     "HE+CLAHE+GC+LT x axial+coronal+sagital over all 582 slices, then recon x3 -> consensus(umbral 2) "
+                     "-> 4x4 confusion counts (configs[2] output side)"),
+        "patients_per_gpu": args.batch,
+        "volume_shape_xyz": [182, 218, 182],
+        "pred_slices_per_plane": args.num_cortes,
+        "l2": "inputs per step (batch x 28.9 MB float32) exceed the 126 MB L2; no flush needed",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import cpu_baseline as CB
+    cores = CB.host_cores()
+    npat = CB.default_sample_patients(cores)
+    with CB.CpuBaseline(npat, cores, num_cortes=args.num_cortes) as cb:
+        for _ in range(args.warmup):
+            cb.step()
+        times = [cb.step() for _ in range(args.steps)]
+        desc = cb.describe()
+    total = sum(times)
+    value = cb.voxels_per_step * args.steps / total / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32+u8 (f64 metrics)", "data": "synthetic",
+        "config": workload_config(args, {"note": "each step is a bounded sample of the workload: "
+                                         f"{npat} patients through the reference's CPU path"}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def build_inputs(args, torch, device, rank):
+    """Distinct synthetic patients resident on `device`.  A handful of CPU-generated base patients
+    (mslesseg_b200.synthetic) are re-scaled per volume on the device so that every
+    volume has its own intensities / per-slice statistics while staying integer-valued."""
+    from mslesseg_b200 import synthetic as S
+    nbase = min(4, args.batch)
+    base = [S.make_patient(1 + n + 100 * rank, config_id=4, num_cortes=args.num_cortes) for n in range(nbase)]
+    bflair = torch.from_numpy(np.stack([p.flair for p in base])).to(device)
+    bgt = torch.from_numpy(np.stack([p.gt for p in base])).to(device)
+    B = args.batch
+    flair = torch.empty((B, 182, 218, 182), dtype=torch.float32, device=device)
+    gt = torch.empty((B, 182, 218, 182), dtype=torch.uint8, device=device)
+    for b in range(B):
+        s = 0.6 + 0.8 * ((b * 0.6180339887) % 1.0)
+        flair[b] = torch.round(bflair[b % nbase] * s) if b >= nbase else bflair[b]
+        gt[b] = bgt[b % nbase]
+    preds = {}
+    for pl in PLANOS:
+        sl = np.concatenate([base[b % nbase].pred_slices[pl] for b in range(B)])
+        vs = np.concatenate([np.full(len(base[b % nbase].pred_indices[pl]), b, np.int32) for b in range(B)])
+        ix = np.concatenate([np.asarray(base[b % nbase].pred_indices[pl], np.int32) for b in range(B)])
+        preds[pl] = (torch.from_numpy(sl).to(device), torch.from_numpy(vs).to(device), torch.from_numpy(ix).to(device))
+    return base, flair, gt, preds
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mslesseg_b200 import _lib, ops, metrics as M, synthetic as S
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    _lib.load()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    B = args.batch
+    base, flair, gt, preds = build_inputs(args, torch, device, rank)
+
+    # pre-allocated outputs (the step allocates nothing)
+    outs = {}
+    for m in MEJORAS:
+        for pl in PLANOS:
+            n_p, rows, cols = ops.plane_dims(pl, 182, 218, 182)
+            outs[(m, pl)] = torch.empty((B, n_p, cols, rows), dtype=torch.uint8, device=device)
+    ws = torch.empty(ops.enhance_volumes_workspace_bytes(B, 182, 218, 182), dtype=torch.uint8, device=device)
+    rvol = {pl: torch.empty((B, 182, 218, 182), dtype=torch.uint8, device=device) for pl in PLANOS}
+    table = torch.zeros((world * B, 4, 4), dtype=torch.int64, device=device)
+    state = {}
+
+    def step():
+        state["flags"] = ops.lesion_slices(gt)
+        ops.enhance_volumes(flair, MEJORAS, PLANOS, outs=outs, workspace=ws)
+        for pl in PLANOS:
+            sl, vs, ix = preds[pl]
+            ops.recon(sl, vs, ix, pl, B, S.SHAPE_XYZ, out=rvol[pl])
+        cons, counts = ops.consensus_eval(rvol["axial"], rvol["coronal"], rvol["sagital"], gt, 2)
+        state["cons"], state["counts"] = cons, counts
+        if world > 1:
+            table.zero_()
+            table[rank * B:(rank + 1) * B] = counts
+            dist.all_reduce(table)            # NCCL SUM of the int64 count table
+        return counts
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = sum(_lib.kernel_launches().values())
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sum(_lib.kernel_launches().values()) - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * B * N_VOX / (ms_per_step * 1e-3) / 1e9
+
+    # ---- per-stage device times (untimed extra passes, CUDA events on the current stream)
+    def time_fn(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    def stage_out():
+        for pl in PLANOS:
+            sl, vs, ix = preds[pl]
+            ops.recon(sl, vs, ix, pl, B, S.SHAPE_XYZ, out=rvol[pl])
+        ops.consensus_eval(rvol["axial"], rvol["coronal"], rvol["sagital"], gt, 2)
+
+    t_in = time_fn(lambda: (ops.lesion_slices(gt), ops.enhance_volumes(flair, MEJORAS, PLANOS, outs=outs, workspace=ws)))
+    t_out = time_fn(stage_out)
+    pred_bytes = sum(int(preds[pl][0].numel()) for pl in PLANOS)
+    stages = {
+        "enhance_slice": {"ms": t_in, "gvoxel_s": B * N_VOX / t_in / 1e6, "algorithmic_bytes_per_voxel": 17,
+                          "gb_s": 17 * B * N_VOX / t_in / 1e6,
+                          "note": "1 B mask read (E0) + 4 B float32 read + 12 x 1 B uint8 written per input voxel"},
+        "recon_consensus_eval": {"ms": t_out, "gvoxel_s": B * N_VOX / t_out / 1e6,
+                                 "algorithmic_bytes": pred_bytes + 5 * B * N_VOX,
+                                 "gb_s": (pred_bytes + 5 * B * N_VOX) / t_out / 1e6,
+                                 "note": "predicted slices present + GT read, 3 recon volumes + consensus written"},
+    }
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events recorded inside the library
+    _lib.profile_enable(True)
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    prof = _lib.profile_collect()
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    npx = {"axial": 182 * 218, "coronal": 182 * 182, "sagital": 218 * 182}
+    chunk = int(os.environ.get("MSL_VOLUME_CHUNK", "4"))
+    nchunks = -(-B // chunk)
+    alg_bytes = {   # algorithmic bytes over ONE step, per kernel kind
+        "enhance_slices_u8_he": 2 * B * N_VOX * 3, "enhance_slices_u8_clahe": 2 * B * N_VOX * 3,
+        "plane_stats_f32": 4 * B * N_VOX, "norm_scatter": (4 + 9) * B * N_VOX, "lesion_flags": B * N_VOX,
+        "recon_gather": pred_bytes + 3 * B * N_VOX, "consensus_eval": 5 * B * N_VOX,
+    }
+    kernels = {}
+    for name, (kms, n) in prof.items():
+        per_step_ms = kms / 2
+        kernels[name] = {"ms_per_step": per_step_ms, "launches_per_step": n // 2}
+        if name in alg_bytes:
+            kernels[name]["gb_s"] = alg_bytes[name] / per_step_ms / 1e6
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    dk = kernels[dom]
+    achieved = dk.get("gb_s", 0.0)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": dk["ms_per_step"] / max(1, dk["launches_per_step"]),
+                "algorithmic_bytes_per_launch": alg_bytes.get(dom, 0) / max(1, dk["launches_per_step"]),
+                "share_of_step": dk["ms_per_step"] / sum(k["ms_per_step"] for k in kernels.values()),
+                "step_level": {"algorithmic_bytes_per_voxel": 22, "gb_s": 22 * B * N_VOX / ms_per_step / 1e6,
+                               "frac": 22 * B * N_VOX / ms_per_step / 1e6 / peak,
+                               "note": "17 B/voxel input side + 5 B/voxel output side (recon volumes counted once)"}}
+
+    # ---- verification of what the timed steps produced (oracle = checker only)
+    verified = None
+    if not args.no_verify and rank == 0:
+        verified = verify(torch, ops, M, S, base, flair, outs, rvol, state)
+
+    # ---- end-to-end with host buffers
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, torch, dist, ops, S, device, world, flair, gt, preds)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_baseline as CB
+        cores = CB.host_cores()
+        with CB.CpuBaseline(CB.default_sample_patients(cores), cores, num_cortes=args.num_cortes) as cb:
+            cb.step()
+            sec = cb.step()
+            cpu = {"value": cb.voxels_per_step / sec / 1e9, "unit": UNIT, "cores": cores, "kind": "port", "sample": cb.describe()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+u8 (int64 counts)", "data": "synthetic", "config": workload_config(args, {"volume_chunk": chunk, "chunks": nchunks}),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "stages": stages, "kernels": kernels, "verified": verified,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def verify(torch, ops, M, S, base, flair, outs, rvol, state):
+    """Spot-check the outputs of the timed steps against the oracle (volume 0 and a re-scaled one)."""
+    import warnings
+    from oracle import oracle as O
+    ok = True
+    for b in (0, flair.shape[0] - 1):
+        vxyz = S.as_xyz(flair[b].cpu().numpy()).astype(np.float64)
+        for pl in PLANOS:
+            n_p = vxyz.shape[O.plane_axis(pl)]
+            for i in (n_p // 2, n_p // 3, 1):
+                for m in MEJORAS:
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")
+                        want = O.png_orient(O.enhance_slice(O.slice_of(vxyz, pl, i), m))
+                    ok &= bool(np.array_equal(outs[(m, pl)][b, i].cpu().numpy(), want))
+    p0 = base[0]
+    gt0 = S.as_xyz(p0.gt)
+    vols = [O.reconstruir(p0.pred_slices[pl], p0.pred_indices[pl], S.SHAPE_XYZ, pl) for pl in PLANOS]
+    for k, pl in enumerate(PLANOS):
+        ok &= bool(np.array_equal(S.as_xyz(rvol[pl][0].cpu().numpy()), vols[k].astype(np.uint8)))
+    cons = O.combinar_volumenes(vols[0].astype(np.float64), vols[1].astype(np.float64), vols[2].astype(np.float64), 2)
+    ok &= bool(np.array_equal(S.as_xyz(state["cons"][0].cpu().numpy()), cons))
+    c = state["counts"][0].cpu().numpy()
+    for k, v in enumerate(vols + [cons]):
+        ok &= c[k].tolist() == list(O.confusion_counts(gt0, v))
+    ok &= M.metricas_desde_conteos(*c[3]) == O.metricas_desde_conteos(*O.confusion_counts(gt0, cons))
+    for k, pl in enumerate(PLANOS):
+        ok &= np.flatnonzero(state["flags"][k][0].cpu().numpy()).tolist() == O.indices_cortes_con_lesion(gt0, pl)
+    return bool(ok)
+
+
+def run_e2e(args, torch, dist, ops, S, device, world, flair, gt, preds):
+    """Same step through the public API with HOST buffers: pinned inputs -> H2D -> kernels -> D2H of every
+    result, chunked over three streams so that copies in both directions overlap the kernels."""
+    B = args.batch
+    CH = 4
+    nstream = 3
+    streams = [torch.cuda.Stream(device=device) for _ in range(nstream)]
+    h_flair = flair.cpu().pin_memory()
+    h_gt = gt.cpu().pin_memory()
+    # per-volume predicted slices (host, pinned)
+    h_pred = {}
+    for pl in PLANOS:
+        sl, vs, ix = (t.cpu() for t in preds[pl])
+        h_pred[pl] = (sl.pin_memory(), vs.numpy(), ix.numpy())
+    dims = {pl: ops.plane_dims(pl, 182, 218, 182) for pl in PLANOS}
+    h_out = {(m, pl): torch.empty((B, dims[pl][0], dims[pl][2], dims[pl][1]), dtype=torch.uint8).pin_memory() for m in MEJORAS for pl in PLANOS}
+    h_rvol = {pl: torch.empty((B, 182, 218, 182), dtype=torch.uint8).pin_memory() for pl in PLANOS}
+    h_cons = torch.empty((B, 182, 218, 182), dtype=torch.uint8).pin_memory()
+    h_counts = torch.empty((B, 4, 4), dtype=torch.int64).pin_memory()
+    bufs = []
+    for _ in range(nstream):
+        d = {"flair": torch.empty((CH, 182, 218, 182), dtype=torch.float32, device=device),
+             "gt": torch.empty((CH, 182, 218, 182), dtype=torch.uint8, device=device),
+             "outs": {(m, pl): torch.empty((CH, dims[pl][0], dims[pl][2], dims[pl][1]), dtype=torch.uint8, device=device) for m in MEJORAS for pl in PLANOS},
+             "ws": torch.empty(ops.enhance_volumes_workspace_bytes(CH, 182, 218, 182), dtype=torch.uint8, device=device),
+             "rvol": {pl: torch.empty((CH, 182, 218, 182), dtype=torch.uint8, device=device) for pl in PLANOS}}
+        bufs.append(d)
+    # slice ranges of each chunk in the concatenated prediction stacks
+    ranges = {}
+    for pl in PLANOS:
+        vs = h_pred[pl][1]
+        ranges[pl] = [(int(np.searchsorted(vs, c0)), int(np.searchsorted(vs, min(c0 + CH, B)))) for c0 in range(0, B, CH)]
+    h2d = d2h = 0
+
+    def e2e_step(count=False):
+        nonlocal h2d, d2h
+        for ci, c0 in enumerate(range(0, B, CH)):
+            n = min(CH, B - c0)
+            st, d = streams[ci % nstream], bufs[ci % nstream]
+            with torch.cuda.stream(st):
+                d["flair"][:n].copy_(h_flair[c0:c0 + n], non_blocking=True)
+                d["gt"][:n].copy_(h_gt[c0:c0 + n], non_blocking=True)
+                fl, g = d["flair"][:n], d["gt"][:n]
+                flags = ops.lesion_slices(g)
+                o = {k: t[:n] for k, t in d["outs"].items()}
+                ops.enhance_volumes(fl, MEJORAS, PLANOS, outs=o, workspace=d["ws"])
+                nb = fl.numel() * 4 + g.numel()
+                for pl in PLANOS:
+                    a, b = ranges[pl][ci]
+                    sl = h_pred[pl][0][a:b].to(device, non_blocking=True)
+                    vs = torch.from_numpy(h_pred[pl][1][a:b] - c0).to(device, non_blocking=True)
+                    ix = torch.from_numpy(h_pred[pl][2][a:b]).to(device, non_blocking=True)
+                    nb += sl.numel() + 8 * (b - a)
+                    ops.recon(sl, vs, ix, pl, n, S.SHAPE_XYZ, out=d["rvol"][pl][:n])
+                cons, counts = ops.consensus_eval(d["rvol"]["axial"][:n], d["rvol"]["coronal"][:n], d["rvol"]["sagital"][:n], g, 2)
+                nd = 0
+                for k, t in o.items():
+                    h_out[k][c0:c0 + n].copy_(t, non_blocking=True); nd += t.numel()
+                for pl in PLANOS:
+                    h_rvol[pl][c0:c0 + n].copy_(d["rvol"][pl][:n], non_blocking=True); nd += n * N_VOX
+                h_cons[c0:c0 + n].copy_(cons, non_blocking=True); nd += cons.numel()
+                h_counts[c0:c0 + n].copy_(counts, non_blocking=True); nd += counts.numel() * 8
+                for f in flags:
+                    nd += f.numel()
+                d["keep"] = (cons, counts, flags)
+                if count:
+                    h2d += nb; d2h += nd
+
+    def sync_all():
+        for st in streams:
+            st.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    e2e_step(); e2e_step(count=True)
+    sync_all()
+    K = max(3, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    sync_all()
+    sec = (time.perf_counter() - t0) / K
+    if world > 1:
+        t = torch.tensor([sec], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    return {"value": world * B * N_VOX / sec / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": sec * 1e3, "steps": K, "note": "pinned host buffers, 4-volume chunks over 3 streams; wall clock around synchronised steps"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -167,6 +167,17 @@ int msl_consensus_eval(const uint8_t* ax, const uint8_t* co, const uint8_t* sa, 
 int msl_confusion_counts(const uint8_t* gt, const uint8_t* pred, int nvol, size_t nvox,
                          int64_t* counts, msl_stream_t stream);
 
+/* ---- instrumentation (not part of the reference surface) ---------------------------------------
+ * msl_kernel_launches: kernels launched by this library since load (total; per kind if non-NULL,
+ * array of msl_kernel_kinds() entries).  msl_profile_enable(1) makes every launch record a pair of
+ * CUDA events on its stream; msl_profile_collect synchronises them, returns milliseconds and launch
+ * counts per kind and switches profiling off.  bench.py uses it for the roofline line. */
+int                msl_kernel_kinds(void);
+const char*        msl_kernel_name(int kind);
+unsigned long long msl_kernel_launches(unsigned long long* per_kind);
+int                msl_profile_enable(int on);
+int                msl_profile_collect(double* ms_per_kind, unsigned long long* n_per_kind);
+
 #ifdef __cplusplus
 }
 #endif

@@ -397,6 +397,7 @@ int launch_enhance_slices(EnhParams p, int dtype, int nslices, cudaStream_t stre
         return MSL_ERR_UNSUPPORTED;
     }
     if (nslices <= 0) return MSL_OK;
+    ProfScope prof((dtype == MSL_F32 ? K_ENH_F32 : K_ENH_U8) + p.mejora, stream);
     if (dtype == MSL_F32) {
         MSL_CUDA_CHECK(cudaFuncSetAttribute(enhance_slices_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         enhance_slices_kernel<float><<<nslices, kThreads, smem, stream>>>(p);

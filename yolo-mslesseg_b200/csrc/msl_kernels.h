@@ -7,6 +7,35 @@
 
 namespace msl {
 
+// Kernel kinds for launch accounting / opt-in event timing (msl_profile.cu).
+enum KernelKind {
+    K_ENH_F32 = 0,        // + mejora (0..4)
+    K_ENH_U8 = 5,         // + mejora (0..4)
+    K_INIT_STATS = 10,
+    K_PLANE_STATS = 11,
+    K_LESION_FLAGS = 12,
+    K_NORM_SCATTER = 13,
+    K_RECON_FILL = 14,
+    K_RECON_SLOT_MAP = 15,
+    K_RECON_GATHER = 16,
+    K_CONSENSUS_EVAL = 17,
+    K_CONFUSION_COUNTS = 18,
+    K_NKIND = 19
+};
+
+// RAII: counts the launch and, when profiling is enabled, brackets it with CUDA events on `stream`.
+class ProfScope {
+public:
+    ProfScope(int kind, cudaStream_t stream);
+    ~ProfScope();
+    ProfScope(const ProfScope&) = delete;
+    ProfScope& operator=(const ProfScope&) = delete;
+private:
+    int kind_;
+    cudaStream_t stream_;
+    cudaEvent_t e0_, e1_;
+};
+
 // One launch of the slice-mode enhancement kernel: `nslices` CTAs, one slice each.
 struct EnhParams {
     const void* in;              // element type given by the launcher's dtype

@@ -244,9 +244,12 @@ int launch_recon(const uint8_t* slices, size_t slice_pitch, const int32_t* vol_o
                  int32_t* slot_of, cudaStream_t stream) {
     const int n_plane = plano == MSL_AXIAL ? Z : (plano == MSL_CORONAL ? Y : X);
     const size_t nmap = (size_t)nvol * n_plane;
+    { ProfScope prof(K_RECON_FILL, stream);
     fill_i32_kernel<<<(unsigned)((nmap + 255) / 256), 256, 0, stream>>>(slot_of, nmap, -1);
+    }
     MSL_LAUNCH_CHECK("fill_i32_kernel");
     if (nslices > 0) {
+        ProfScope prof(K_RECON_SLOT_MAP, stream);
         slot_map_kernel<<<(nslices + 255) / 256, 256, 0, stream>>>(vol_of_slice, idx_of_slice, nslices, nvol, n_plane, slot_of);
         MSL_LAUNCH_CHECK("slot_map_kernel");
     }
@@ -256,6 +259,7 @@ int launch_recon(const uint8_t* slices, size_t slice_pitch, const int32_t* vol_o
     const int W = plano == MSL_AXIAL ? Y : Z;
     const int T = plano == MSL_AXIAL ? Z : Y;
     dim3 grid(((X + kTile - 1) / kTile) * ((W + kTile - 1) / kTile), T, nvol);
+    ProfScope prof(K_RECON_GATHER, stream);
     recon_gather_kernel<<<grid, 256, 0, stream>>>(a);
     MSL_LAUNCH_CHECK("recon_gather_kernel");
     return MSL_OK;
@@ -268,6 +272,7 @@ int launch_consensus_eval(const uint8_t* ax, const uint8_t* co, const uint8_t* s
     a.ax = ax; a.co = co; a.sa = sa; a.gt = gt; a.consenso = consenso; a.counts = counts; a.nvox = nvox; a.umbral = umbral;
     dim3 grid(chunks_for(nvox, nvol), nvol);
     const bool vec = (nvox % 8 == 0) && aligned8(ax) && aligned8(co) && aligned8(sa) && aligned8(gt) && aligned8(consenso);
+    ProfScope prof(K_CONSENSUS_EVAL, stream);
     if (vec) consensus_eval_kernel<true><<<grid, kCntThreads, 0, stream>>>(a);
     else consensus_eval_kernel<false><<<grid, kCntThreads, 0, stream>>>(a);
     MSL_LAUNCH_CHECK("consensus_eval_kernel");
@@ -279,6 +284,7 @@ int launch_confusion_counts(const uint8_t* gt, const uint8_t* pred, int nvol, si
     MSL_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)nvol * 4 * sizeof(long long), stream));
     dim3 grid(chunks_for(nvox, nvol), nvol);
     const bool vec = (nvox % 8 == 0) && aligned8(gt) && aligned8(pred);
+    ProfScope prof(K_CONFUSION_COUNTS, stream);
     if (vec) confusion_counts_kernel<true><<<grid, kCntThreads, 0, stream>>>(gt, pred, nvox, counts);
     else confusion_counts_kernel<false><<<grid, kCntThreads, 0, stream>>>(gt, pred, nvox, counts);
     MSL_LAUNCH_CHECK("confusion_counts_kernel");

@@ -44,6 +44,11 @@ _SIGNATURES = {
     "msl_recon": (C.c_int, [_vp, _sz, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "msl_consensus_eval": (C.c_int, [_vp, _vp, _vp, _vp, _i, _sz, _i, _vp, _vp, _vp]),
     "msl_confusion_counts": (C.c_int, [_vp, _vp, _i, _sz, _vp, _vp]),
+    "msl_kernel_kinds": (C.c_int, []),
+    "msl_kernel_name": (C.c_char_p, [_i]),
+    "msl_kernel_launches": (C.c_ulonglong, [C.POINTER(C.c_ulonglong)]),
+    "msl_profile_enable": (C.c_int, [_i]),
+    "msl_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
 }
 
 _lib = None
@@ -75,3 +80,26 @@ def check(rc: int) -> None:
     if rc != OK:
         msg = load().msl_last_error()
         raise MslError(rc, msg.decode("utf-8", "replace") if msg else "")
+
+
+def kernel_launches() -> dict:
+    """{kernel kind name: launches since the library was loaded}."""
+    lib = load()
+    n = lib.msl_kernel_kinds()
+    arr = (C.c_ulonglong * n)()
+    lib.msl_kernel_launches(arr)
+    return {lib.msl_kernel_name(k).decode(): int(arr[k]) for k in range(n)}
+
+
+def profile_enable(on: bool = True) -> None:
+    check(load().msl_profile_enable(1 if on else 0))
+
+
+def profile_collect() -> dict:
+    """{kernel kind name: (milliseconds, launches)} for the launches since profile_enable()."""
+    lib = load()
+    n = lib.msl_kernel_kinds()
+    ms = (C.c_double * n)()
+    cnt = (C.c_ulonglong * n)()
+    check(lib.msl_profile_collect(ms, cnt))
+    return {lib.msl_kernel_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n) if cnt[k]}
