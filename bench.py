@@ -293,8 +293,8 @@ def run_ours(args):
     chunk = int(os.environ.get("MSL_VOLUME_CHUNK", "4"))
     nchunks = -(-B // chunk)
     alg_bytes = {   # algorithmic bytes over ONE step, per kernel kind
-        "enhance_slices_u8_he": 2 * B * N_VOX * 3, "enhance_slices_u8_clahe": 2 * B * N_VOX * 3,
-        "plane_stats_f32": 4 * B * N_VOX, "norm_scatter": (4 + 9) * B * N_VOX, "lesion_flags": B * N_VOX,
+        "enhance_dense": (1 + 4) * 3 * B * N_VOX,      # per plane: staged uint8 slice in, HE + CLAHE + GC + LT out
+        "plane_stats_f32": 4 * B * N_VOX, "norm_scatter": (4 + 3) * B * N_VOX, "lesion_flags": B * N_VOX,
         "recon_gather": pred_bytes + 3 * B * N_VOX, "consensus_eval": 5 * B * N_VOX,
     }
     kernels = {}

@@ -77,6 +77,12 @@ int msl_version(void) { return MSL_ABI_VERSION; }
 
 const char* msl_last_error(void) { return g_err; }
 
+// bytes of the three staged uint8 slice stacks for ONE volume (16-byte slice pitch, 256-byte stack pitch)
+static size_t u_stack_bytes_per_volume(int X, int Y, int Z) {
+    const size_t ax = (size_t)Z * dense_u_pitch(X * Y), co = (size_t)Y * dense_u_pitch(X * Z), sa = (size_t)X * dense_u_pitch(Y * Z);
+    return ((ax + 255) & ~(size_t)255) + ((co + 255) & ~(size_t)255) + ((sa + 255) & ~(size_t)255);
+}
+
 static int enhance_chunk_volumes(void) {
     const char* e = getenv("MSL_VOLUME_CHUNK");
     int c = e ? atoi(e) : 4;
@@ -91,7 +97,8 @@ size_t msl_workspace_bytes(int op, int nvol, int X, int Y, int Z) {
             size_t stats = (((size_t)nvol * (X + Y + Z) * 2 * sizeof(unsigned)) + 255) & ~(size_t)255;
             int chunk = enhance_chunk_volumes();
             if (chunk > nvol) chunk = nvol;
-            return stats + 3 * (size_t)chunk * ((N + 255) & ~(size_t)255);
+            (void)N;
+            return stats + (size_t)chunk * u_stack_bytes_per_volume(X, Y, Z);
         }
         case MSL_WS_RECON: {
             int m = X > Y ? X : Y;
@@ -171,26 +178,32 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z, uint8_t
     cudaStream_t stream = (cudaStream_t)stream_;
     const size_t need = msl_workspace_bytes(MSL_WS_ENHANCE_VOLUMES, nvol, X, Y, Z);
     if (!ws || ws_bytes < need) { set_error("workspace of %zu bytes needed, %zu given", need, ws_bytes); return MSL_ERR_WORKSPACE; }
-    bool any = false, need_u = false;
+    bool any = false;
     for (int k = 0; k < 12; ++k) any |= outs[k] != nullptr;
-    for (int k = 0; k < 6; ++k) need_u |= outs[k] != nullptr;     // HE (0-2) and CLAHE (3-5) consume the normalised stacks
     if (!any) return MSL_OK;
 
     const size_t N = (size_t)X * Y * Z;
     const size_t nsl = (size_t)nvol * (X + Y + Z);
     unsigned* stats = reinterpret_cast<unsigned*>(ws);
     const size_t stats_bytes = ((nsl * 2 * sizeof(unsigned)) + 255) & ~(size_t)255;
-    const size_t ustride = (N + 255) & ~(size_t)255;
     int chunk = enhance_chunk_volumes();
     if (chunk > nvol) chunk = nvol;
-    uint8_t* ubase = reinterpret_cast<uint8_t*>(ws) + stats_bytes;
-    uint8_t* U[3] = {ubase, ubase + (size_t)chunk * ustride, ubase + 2 * (size_t)chunk * ustride};
-    // NB: the three U stacks are densely packed per chunk: [chunk][n_p][cols][rows] = chunk * N bytes each.
+    const int n_p[3] = {Z, Y, X};
+    const int rows_p[3] = {X, X, Y}, cols_p[3] = {Y, Z, Z};
+    // staged normalised stacks, PNG orientation, slice pitch padded to 16 bytes: [chunk][n_p][u_pitch]
+    size_t upitch[3];
+    uint8_t* U[3];
+    {
+        uint8_t* cur = reinterpret_cast<uint8_t*>(ws) + stats_bytes;
+        for (int pl = 0; pl < 3; ++pl) {
+            upitch[pl] = dense_u_pitch(rows_p[pl] * cols_p[pl]);
+            U[pl] = cur;
+            cur += (((size_t)n_p[pl] * upitch[pl] + 255) & ~(size_t)255) * (size_t)chunk;
+        }
+    }
 
     int rc = launch_init_stats(stats, nsl, stream);
     if (rc) return rc;
-    const int n_p[3] = {Z, Y, X};
-    const int rows_p[3] = {X, X, Y}, cols_p[3] = {Y, Z, Z};
     for (int v0 = 0; v0 < nvol; v0 += chunk) {
         const int nv = (nvol - v0) < chunk ? (nvol - v0) : chunk;
         const float* cvol = vol + (size_t)v0 * N;
@@ -200,28 +213,43 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z, uint8_t
         ScatterOuts so;
         memset(&so, 0, sizeof(so));
         for (int pl = 0; pl < 3; ++pl) {
-            if (need_u) so.o[0][pl] = U[pl];
-            if (outs[(MSL_MEJORA_GC - 1) * 3 + pl]) so.o[1][pl] = outs[(MSL_MEJORA_GC - 1) * 3 + pl] + (size_t)v0 * N;
-            if (outs[(MSL_MEJORA_LT - 1) * 3 + pl]) so.o[2][pl] = outs[(MSL_MEJORA_LT - 1) * 3 + pl] + (size_t)v0 * N;
+            bool want = false;
+            for (int mej = MSL_MEJORA_HE; mej <= MSL_MEJORA_LT; ++mej) want |= outs[(mej - 1) * 3 + pl] != nullptr;
+            if (want) { so.u[pl] = U[pl]; so.pitch[pl] = upitch[pl]; }
         }
-        // only stage the normalised plane stacks that HE / CLAHE will actually read
-        for (int pl = 0; pl < 3; ++pl)
-            if (!outs[(MSL_MEJORA_HE - 1) * 3 + pl] && !outs[(MSL_MEJORA_CLAHE - 1) * 3 + pl]) so.o[0][pl] = nullptr;
-        rc = launch_norm_scatter(cvol, nv, X, Y, Z, cstats, so, tables, stream);
+        rc = launch_norm_scatter(cvol, nv, X, Y, Z, cstats, so, stream);
         if (rc) return rc;
-        for (int mej = MSL_MEJORA_HE; mej <= MSL_MEJORA_CLAHE; ++mej) {
-            for (int pl = 0; pl < 3; ++pl) {
-                uint8_t* dst = outs[(mej - 1) * 3 + pl];
-                if (!dst) continue;
-                // the staged stack is in PNG orientation: G[a, b] = P[cols-1-b, a]
-                EnhParams p;
-                memset(&p, 0, sizeof(p));
-                const int rows = rows_p[pl], cols = cols_p[pl], npx = rows * cols;
+        for (int pl = 0; pl < 3; ++pl) {
+            if (!so.u[pl]) continue;
+            uint8_t* dst[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+            uintptr_t align = 0;
+            for (int mej = MSL_MEJORA_HE; mej <= MSL_MEJORA_LT; ++mej) {
+                uint8_t* o = outs[(mej - 1) * 3 + pl];
+                dst[mej] = o ? o + (size_t)v0 * N : nullptr;
+                align |= reinterpret_cast<uintptr_t>(dst[mej]);
+            }
+            const int rows = rows_p[pl], cols = cols_p[pl], npx = rows * cols;
+            EnhParams p;
+            memset(&p, 0, sizeof(p));
+            clahe_geometry(rows, cols, p);
+            const bool dense_ok = (npx % 4 == 0) && rows >= 2 && (align & 3) == 0 &&
+                                  (unsigned long long)npx * (unsigned)rows < 0x100000000ull &&
+                                  2560 + (size_t)(rows + cols) * 16 + 65536 + dense_u_pitch(npx) <= 227 * 1024;
+            if (dense_ok) {
+                rc = launch_enhance_dense(U[pl], upitch[pl], nv * n_p[pl], rows, cols, dst[MSL_MEJORA_HE], dst[MSL_MEJORA_CLAHE],
+                                          dst[MSL_MEJORA_GC], dst[MSL_MEJORA_LT], tables, p.cl_th, p.cl_tw, p.cl_clip, p.cl_lut_scale, stream);
+                if (rc) return rc;
+                continue;
+            }
+            // generic slice kernel on the staged stack (PNG orientation: G[a, b] = P[cols-1-b, a])
+            for (int mej = MSL_MEJORA_HE; mej <= MSL_MEJORA_LT; ++mej) {
+                if (!dst[mej]) continue;
                 p.in = U[pl];
-                p.vol_stride = (long long)n_p[pl] * npx; p.idx_stride = npx; p.base0 = (long long)(cols - 1) * rows;
+                p.vol_stride = (long long)n_p[pl] * (long long)upitch[pl]; p.idx_stride = (long long)upitch[pl];
+                p.base0 = (long long)(cols - 1) * rows;
                 p.sa = 1; p.sb = -(long long)rows; p.rows = rows; p.cols = cols; p.nvol = nv; p.n_plane = n_p[pl];
-                p.out = dst + (size_t)v0 * N; p.out_pitch = npx; p.layout = MSL_OUT_P; p.mejora = mej; p.tables = tables;
-                clahe_geometry(rows, cols, p);
+                p.vol_of_slice = nullptr; p.idx_of_slice = nullptr;
+                p.out = dst[mej]; p.out_pitch = npx; p.layout = MSL_OUT_P; p.mejora = mej; p.tables = tables;
                 rc = launch_enhance_slices(p, MSL_U8, nv * n_p[pl], stream);
                 if (rc) return rc;
             }

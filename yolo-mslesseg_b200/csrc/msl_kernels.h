@@ -20,7 +20,8 @@ enum KernelKind {
     K_RECON_GATHER = 16,
     K_CONSENSUS_EVAL = 17,
     K_CONFUSION_COUNTS = 18,
-    K_NKIND = 19
+    K_ENH_DENSE = 19,     // fused HE + CLAHE + GC + LT over staged uint8 stacks
+    K_NKIND = 20
 };
 
 // RAII: counts the launch and, when profiling is enabled, brackets it with CUDA events on `stream`.
@@ -70,14 +71,20 @@ int launch_plane_stats_f32(const float* vol, int nvol, int X, int Y, int Z, unsi
 int launch_lesion_flags(const void* gt, int dtype, int nvol, int X, int Y, int Z,
                         uint8_t* any_ax, uint8_t* any_co, uint8_t* any_sa, cudaStream_t stream);
 
-// Normalise each voxel with the (min, ptp) of the three slices it belongs to and scatter the bytes
-// into three PNG-oriented slice stacks; up to three point-wise tables per voxel (identity/GC/LT).
+// Normalise each voxel with the (min, ptp) of the three slices it belongs to and scatter the bytes into
+// three PNG-oriented uint8 slice stacks (axial, coronal, sagital); NULL = skip that plane.
 struct ScatterOuts {
-    // per variant (0 = normalised u, 1 = GC, 2 = LT) and plane; NULL = skip
-    uint8_t* o[3][3];
+    uint8_t* u[3];
+    size_t pitch[3];             // bytes between consecutive slices of that stack
 };
 int launch_norm_scatter(const float* vol, int nvol, int X, int Y, int Z, const unsigned* stats,
-                        const ScatterOuts& outs, const uint8_t* tables, cudaStream_t stream);
+                        const ScatterOuts& outs, cudaStream_t stream);
+
+// Dense HE / CLAHE over PNG-oriented uint8 stacks (msl_enhance_dense.cu)
+size_t dense_u_pitch(int npx);
+int launch_enhance_dense(const uint8_t* U, size_t u_pitch, int nslices, int rows, int cols,
+                         uint8_t* out_he, uint8_t* out_clahe, uint8_t* out_gc, uint8_t* out_lt, const uint8_t* tables,
+                         int th, int tw, int clip, float lut_scale, cudaStream_t stream);
 
 // R1-R2
 int launch_recon(const uint8_t* slices, size_t slice_pitch, const int32_t* vol_of_slice, const int32_t* idx_of_slice,

@@ -21,7 +21,7 @@ const char* const kNames[K_NKIND] = {
     "enhance_slices_f32_none", "enhance_slices_f32_he", "enhance_slices_f32_clahe", "enhance_slices_f32_gc", "enhance_slices_f32_lt",
     "enhance_slices_u8_none", "enhance_slices_u8_he", "enhance_slices_u8_clahe", "enhance_slices_u8_gc", "enhance_slices_u8_lt",
     "init_stats", "plane_stats_f32", "lesion_flags", "norm_scatter",
-    "recon_fill", "recon_slot_map", "recon_gather", "consensus_eval", "confusion_counts",
+    "recon_fill", "recon_slot_map", "recon_gather", "consensus_eval", "confusion_counts", "enhance_dense",
 };
 }  // namespace
 
