@@ -103,7 +103,7 @@ size_t msl_workspace_bytes(int op, int nvol, int X, int Y, int Z) {
         case MSL_WS_RECON: {
             int m = X > Y ? X : Y;
             if (Z > m) m = Z;
-            return (size_t)nvol * m * sizeof(int32_t);
+            return (size_t)nvol * (m + 2) * sizeof(int32_t);      // inverse slice map + first/last present index
         }
         default:
             return 0;

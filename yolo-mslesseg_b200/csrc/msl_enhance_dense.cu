@@ -166,32 +166,69 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
     if (!DO_CLAHE) return;
 
     // ---------------------------------------------------------------- CLAHE: tile histograms
+    // Tile maps: ty of every P column c (slice row a) and tx of every P row r (slice column b = cols-1-r),
+    // written into the not-yet-used tail of the interpolation tables' neighbourhood (misc scratch is too small):
+    // they live in the first bytes of the upper half of R (the float LUT area is only needed after the CDFs).
     const int th = p.th, tw = p.tw;
     unsigned* hist = reinterpret_cast<unsigned*>(R);        // 64 tiles x 128 words (two 16-bit bins per word)
-    for (int t = warp; t < 64; t += kWarps) {
-        const int ty = t >> 3, tx = t & 7;
-        unsigned* ht = hist + t * 128;
-        int zeros = 0;
-        for (int l0 = 0; l0 < th; l0 += 32) {
-            const int l = l0 + lane;
-            const bool ok = l < th;
-            const int a = ok ? reflect101(ty * th + l, rows) : 0;          // P column
-            for (int bb = 0; bb < tw; ++bb) {
-                const int b = reflect101(tx * tw + bb, cols);
-                const int r = cols - 1 - b;
-                int L = 0;
-                if (ok) L = lutl[su[r * W + a]];
-                const bool z = ok && L == 0;
-                zeros += __popc(__ballot_sync(FULL, z));
-                if (ok && !z) atomicAdd(&ht[L >> 1], 1u << ((L & 1) * 16));
+    uint8_t* tya = R + 32768;                                // [rows]
+    uint8_t* txr = tya + ((rows + 3) & ~3);                  // [cols]
+    for (int a = tid; a < rows; a += kThreads) tya[a] = (uint8_t)(a / th);
+    for (int r = tid; r < cols; r += kThreads) txr[r] = (uint8_t)((cols - 1 - r) / tw);
+    __syncthreads();
+    {
+        // real pixels: linear over the smem words, L = LUT_L[u]; zero words (background) cost one atomic
+        const uint32_t* su32 = reinterpret_cast<const uint32_t*>(su);
+        const int nw = npx >> 2;
+        for (int q = tid; q < nw; q += kThreads) {
+            const unsigned o = 4u * q;
+            int r = (int)__umulhi(o, p.magic_w);
+            int c = (int)o - r * W;
+            const uint32_t w = su32[q];
+            if (c + 3 < W) {
+                const int tx = txr[r];
+                const int t0 = tya[c] * 8 + tx, t3 = tya[c + 3] * 8 + tx;
+                if (w == 0 && t0 == t3) { atomicAdd(&hist[t0 * 128], 4u); continue; }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int L = lutl[(w >> (8 * k)) & 0xff];
+                    const int t = (k == 0) ? t0 : (k == 3 ? t3 : tya[c + k] * 8 + tx);
+                    atomicAdd(&hist[t * 128 + (L >> 1)], 1u << ((L & 1) * 16));
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int L = lutl[(w >> (8 * k)) & 0xff];
+                    atomicAdd(&hist[(tya[c] * 8 + txr[r]) * 128 + (L >> 1)], 1u << ((L & 1) * 16));
+                    if (++c == W) { c = 0; ++r; }
+                }
             }
         }
-        __syncwarp();
-        // clip + redistribute + CDF -> tile LUT over L (OpenCV CLAHE_CalcLut_Body)
+        for (int o = (nw << 2) + tid; o < npx; o += kThreads) {
+            const int r = o / W, c = o - r * W, L = lutl[su[o]];
+            atomicAdd(&hist[(tya[c] * 8 + txr[r]) * 128 + (L >> 1)], 1u << ((L & 1) * 16));
+        }
+        // BORDER_REFLECT_101 padding (OpenCV pads bottom / right up to 8 tiles): the few padded pixels
+        const int prow = th * 8, pcol = tw * 8;
+        const int nA = (prow - rows) * pcol;                 // padded slice rows, all padded columns
+        const int nB = rows * (pcol - cols);                 // real slice rows, padded columns
+        for (int i = tid; i < nA + nB; i += kThreads) {
+            int ap, bp;
+            if (i < nA) { ap = rows + i / pcol; bp = i % pcol; }
+            else { const int j = i - nA, wp = pcol - cols; ap = j / wp; bp = cols + j % wp; }
+            const int a = reflect101(ap, rows), b = reflect101(bp, cols);
+            const int L = lutl[su[(cols - 1 - b) * W + a]];
+            atomicAdd(&hist[((ap / th) * 8 + bp / tw) * 128 + (L >> 1)], 1u << ((L & 1) * 16));
+        }
+    }
+    __syncthreads();
+    // ---------------------------------------------------------------- CLAHE: clip + redistribute + CDF -> tile LUTs
+    // (OpenCV CLAHE_CalcLut_Body).  One warp per tile, 8 bins per lane.
+    for (int t = warp; t < 64; t += kWarps) {
+        unsigned* ht = hist + t * 128;
         uint4 w4 = reinterpret_cast<const uint4*>(ht)[lane];
         int hb[8] = {(int)(w4.x & 0xffff), (int)(w4.x >> 16), (int)(w4.y & 0xffff), (int)(w4.y >> 16),
                      (int)(w4.z & 0xffff), (int)(w4.z >> 16), (int)(w4.w & 0xffff), (int)(w4.w >> 16)};
-        if (lane == 0) hb[0] += zeros;
         const int clip = p.clip;
         int clipped = 0;
 #pragma unroll
@@ -200,13 +237,17 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
         clipped = warp_sum(clipped);
         const int rb = clipped / 256;
         const int res = clipped - rb * 256;
-        const int step = res > 0 ? max(256 / res, 1) : 1;
+        // residual: bins 0, step, 2*step, ... (res of them) get one more; walk this lane's 8 bins without dividing per bin
+        const int step = res > 0 ? max(256 / res, 1) : 256;
+        const int base = lane * 8;
+        int kn = (base + step - 1) / step;                   // index of the first multiple of step that is >= base
+        int nxt = kn * step;
         int run = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int bin = lane * 8 + k;
             hb[k] += rb;
-            if (res > 0 && (bin % step) == 0 && (bin / step) < res) hb[k] += 1;
+            const bool hit = (nxt == base + k) && (kn < res);
+            if (hit) { hb[k] += 1; nxt += step; ++kn; }
             run += hb[k];
             hb[k] = run;
         }
@@ -262,38 +303,29 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
     }
     __syncthreads();
 
-    // ---------------------------------------------------------------- CLAHE: bilinear blend + LUT_OUT + store
-    uint8_t* out = p.out_clahe + s * p.out_pitch;
-    const uint32_t* su32 = reinterpret_cast<const uint32_t*>(su);
-    uint32_t* out32 = reinterpret_cast<uint32_t*>(out);
-    const int nw = npx >> 2;
-    auto blend = [&](uint32_t v, const XY& X, const XY& Y) -> uint32_t {
-        const float* F1 = F + Y.o1 + v;
-        const float* F2 = F + Y.o2 + v;
+    // ---------------------------------------------------------------- CLAHE: bilinear blend + LUT_OUT, in place
+    // Consecutive lanes take consecutive pixels (conflict-free table reads); the result byte replaces u in smem.
+    for (int o = tid; o < npx; o += kThreads) {
+        const int r = (int)__umulhi((unsigned)o, p.magic_w);
+        const int c = o - r * W;
+        const XY X = xtab[r];
+        const XY Y = ytab[c];
+        const float* F1 = F + Y.o1 + su[o];
+        const float* F2 = F1 + (Y.o2 - Y.o1);
         float top = __fadd_rn(__fmul_rn(F1[X.o1], X.w1), __fmul_rn(F1[X.o2], X.w));
         float bot = __fadd_rn(__fmul_rn(F2[X.o1], X.w1), __fmul_rn(F2[X.o2], X.w));
         float res = __fadd_rn(__fmul_rn(top, Y.w1), __fmul_rn(bot, Y.w));
         // cvRound (half-even) of a value in [0, 255.0001]: the low mantissa bits of res + 1.5 * 2^23
-        uint32_t i = __float_as_uint(__fadd_rn(res, 12582912.0f)) & 0xffu;
-        return lutout[i];
-    };
-    for (int q = tid; q < nw; q += kThreads) {
-        const unsigned o = 4u * q;
-        int r = (int)__umulhi(o, p.magic_w);
-        int c = (int)o - r * W;
-        XY X = xtab[r];
-        const uint32_t w = su32[q];
-        uint32_t pk = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            pk |= blend((w >> (8 * k)) & 0xff, X, ytab[c]) << (8 * k);
-            if (++c == W) { c = 0; ++r; if (r < cols) X = xtab[r]; }
-        }
-        out32[q] = pk;
+        su[o] = lutout[__float_as_uint(__fadd_rn(res, 12582912.0f)) & 0xffu];
     }
-    for (int o = (nw << 2) + tid; o < npx; o += kThreads) {
-        int r = o / W, c = o - r * W;
-        out[o] = (uint8_t)blend(su[o], xtab[r], ytab[c]);
+    __syncthreads();
+    {
+        uint8_t* out = p.out_clahe + s * p.out_pitch;
+        const uint32_t* su32 = reinterpret_cast<const uint32_t*>(su);
+        uint32_t* out32 = reinterpret_cast<uint32_t*>(out);
+        const int nw = npx >> 2;
+        for (int q = tid; q < nw; q += kThreads) out32[q] = su32[q];
+        for (int o = (nw << 2) + tid; o < npx; o += kThreads) out[o] = su[o];
     }
 }
 

@@ -18,81 +18,132 @@ namespace msl {
 namespace {
 
 // ------------------------------------------------------------------------------------ recon
-__global__ void fill_i32_kernel(int32_t* p, size_t n, int32_t val) {
+// Volumes are zero-filled by cudaMemsetAsync; only the slices that exist are written (typically ~20 % of the
+// indices of a plane: Paciente.indices_a_usar keeps a central window of the lesion slices).
+__global__ void recon_init_kernel(int32_t* slot_of, size_t nmap, int32_t* xrange, int nvol) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = val;
+    if (i < nmap) slot_of[i] = -1;
+    if (i < (size_t)nvol) { xrange[2 * i] = 0x7fffffff; xrange[2 * i + 1] = -1; }
 }
 
 __global__ void slot_map_kernel(const int32_t* __restrict__ vol_of_slice, const int32_t* __restrict__ idx_of_slice,
-                                int nslices, int nvol, int n_plane, int32_t* __restrict__ slot_of) {
+                                int nslices, int nvol, int n_plane, int32_t* __restrict__ slot_of, int32_t* __restrict__ xrange) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nslices) return;
     int v = vol_of_slice[s], i = idx_of_slice[s];
     if (v < 0 || v >= nvol || i < 0 || i >= n_plane) return;
     atomicMax(&slot_of[(size_t)v * n_plane + i], s);     // duplicate index: the later slice wins
+    atomicMin(&xrange[2 * v], i);
+    atomicMax(&xrange[2 * v + 1], i);
 }
-
-constexpr int kTile = 64;
-constexpr int kTilePitch = 68;     // 17 words: conflict-free column reads
 
 struct ReconArgs {
     const uint8_t* slices;
     size_t slice_pitch;
+    const int32_t* vol_of_slice;
+    const int32_t* idx_of_slice;
     const int32_t* slot_of;
+    const int32_t* xrange;
     uint8_t* vol_u8;
     float* vol_f32;
-    int X, Y, Z, plano;
+    int X, Y, Z, plano, nvol;
 };
 
-// grid (tiles_x * tiles_w, T, nvol); block 256.
-//   axial   : T = Z (t = z), w = y   src = slice(z)[x * Y + y]
-//   coronal : T = Y (t = y), w = z   src = slice(y)[x * Z + z]
-//   sagital : T = Y (t = y), w = z   src = slice(x)[y * Z + z]
-__global__ void __launch_bounds__(256) recon_gather_kernel(const ReconArgs a) {
-    __shared__ uint8_t tile[kTile][kTilePitch];
+// Axial / coronal: one CTA per PRESENT slice.  The slice Q[x][w] (w = y for axial, z for coronal; w fastest) is
+// binarised and transposed into shared memory, then written as x-contiguous rows of the volume:
+//   axial   slice k: out[v][k][w][x]     coronal slice j: out[v][w][j][x]
+// grid (nslices); block 256.  PAIR: 16-bit accesses (X and the slice row length even, 2-byte aligned bases).
+template <bool PAIR>
+__global__ void __launch_bounds__(256) recon_rows_kernel(const ReconArgs a) {
+    extern __shared__ __align__(16) uint8_t T[];          // [W][tp]  transposed, binarised slice
     const int X = a.X, Y = a.Y, Z = a.Z;
-    const int W = a.plano == MSL_AXIAL ? Y : Z;
-    const int n_plane = a.plano == MSL_AXIAL ? Z : (a.plano == MSL_CORONAL ? Y : X);
-    const int tiles_x = (X + kTile - 1) / kTile;
-    const int tx = blockIdx.x % tiles_x, tw = blockIdx.x / tiles_x;
-    const int x0 = tx * kTile, w0 = tw * kTile;
-    const int t = blockIdx.y, v = blockIdx.z;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int32_t* slot_v = a.slot_of + (size_t)v * n_plane;
-
-    int slot_t = a.plano == MSL_SAGITAL ? 0 : slot_v[t];
-    for (int xr = warp; xr < kTile; xr += 8) {
-        const int x = x0 + xr;
-        int slot = -1;
-        size_t base = 0;
-        if (x < X) {
-            if (a.plano == MSL_SAGITAL) { slot = slot_v[x]; base = (size_t)t * W; }
-            else { slot = slot_t; base = (size_t)x * W; }
+    const int s = blockIdx.x;
+    const int v = a.vol_of_slice[s], idx = a.idx_of_slice[s];
+    const int n_plane = a.plano == MSL_AXIAL ? Z : Y;
+    if (v < 0 || v >= a.nvol || idx < 0 || idx >= n_plane) return;
+    if (a.slot_of[(size_t)v * n_plane + idx] != s) return;          // superseded duplicate
+    const int W = a.plano == MSL_AXIAL ? Y : Z;           // slice row length (cols), number of output rows
+    const int tp = (X + 4) & ~1;                          // smem pitch: even and not a multiple of 4 words apart
+    const uint8_t* src = a.slices + (size_t)s * a.slice_pitch;
+    const int tid = threadIdx.x;
+    if (PAIR) {
+        const uint16_t* src2 = reinterpret_cast<const uint16_t*>(src);
+        const int wp = W >> 1;
+        for (int q = tid; q < X * wp; q += 256) {
+            const int x = q / wp, w = 2 * (q - x * wp);
+            const uint32_t u = __ldg(src2 + q);
+            T[w * tp + x] = (u & 0xff) ? 1 : 0;
+            T[(w + 1) * tp + x] = (u >> 8) ? 1 : 0;
         }
-        const uint8_t* src = a.slices + (slot < 0 ? 0 : (size_t)slot * a.slice_pitch) + base;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int w = w0 + h * 32 + lane;
-            uint8_t q = 0;
-            if (slot >= 0 && w < W) q = __ldg(src + w) > 0 ? 1 : 0;
-            tile[xr][h * 32 + lane] = q;
+    } else {
+        for (int q = tid; q < X * W; q += 256) {
+            const int x = q / W, w = q - x * W;
+            T[w * tp + x] = __ldg(src + q) ? 1 : 0;
         }
     }
     __syncthreads();
-    for (int wr = warp; wr < kTile; wr += 8) {
-        const int w = w0 + wr;
-        if (w >= W) break;
-        const int z = a.plano == MSL_AXIAL ? t : w;
-        const int y = a.plano == MSL_AXIAL ? w : t;
-        const size_t off = (((size_t)v * Z + z) * Y + y) * X;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int xr = h * 32 + lane, x = x0 + xr;
-            if (x < X) {
-                uint8_t q = tile[xr][wr];
-                if (a.vol_u8) a.vol_u8[off + x] = q;
-                if (a.vol_f32) a.vol_f32[off + x] = (float)q;
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int w = warp; w < W; w += 8) {
+        const size_t off = a.plano == MSL_AXIAL ? (((size_t)v * Z + idx) * Y + w) * X : (((size_t)v * Z + w) * Y + idx) * X;
+        if (a.vol_u8) {
+            if (PAIR) {
+                uint16_t* dst = reinterpret_cast<uint16_t*>(a.vol_u8 + off);
+                const uint16_t* row = reinterpret_cast<const uint16_t*>(T + w * tp);
+                for (int j = lane; j < (X >> 1); j += 32) dst[j] = row[j];
+            } else {
+                for (int x = lane; x < X; x += 32) a.vol_u8[off + x] = T[w * tp + x];
             }
+        }
+        if (a.vol_f32)
+            for (int x = lane; x < X; x += 32) a.vol_f32[off + x] = (float)T[w * tp + x];
+    }
+}
+
+// Sagital: out[v][z][y][x] = Q_x[y][z] - the slice index is the volume's FASTEST axis, so slices are gathered
+// through 64 (x) x 64 (z) byte tiles; only tiles that overlap the range of present slices do any work.
+constexpr int kTile = 64;
+constexpr int kTilePitch = 68;     // 17 words: conflict-free column reads
+
+// grid (tiles_x * tiles_z, Y, nvol); block 256.
+__global__ void __launch_bounds__(256) recon_sagital_kernel(const ReconArgs a) {
+    __shared__ __align__(4) uint8_t tile[kTile][kTilePitch];
+    const int X = a.X, Y = a.Y, Z = a.Z;
+    const int tiles_x = (X + kTile - 1) / kTile;
+    const int tx = blockIdx.x % tiles_x, tz = blockIdx.x / tiles_x;
+    const int x0 = tx * kTile, z0 = tz * kTile;
+    const int y = blockIdx.y, v = blockIdx.z;
+    const int xmin = a.xrange[2 * v], xmax = a.xrange[2 * v + 1];
+    if (xmax < x0 || xmin >= x0 + kTile) return;          // no present slice in this tile: the memset already wrote it
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int32_t* slot_v = a.slot_of + (size_t)v * X;
+    const bool even = ((a.slice_pitch | (size_t)Z | reinterpret_cast<uintptr_t>(a.slices)) & 1) == 0;
+    for (int xr = warp; xr < kTile; xr += 8) {
+        const int x = x0 + xr;
+        const int slot = x < X ? slot_v[x] : -1;
+        const uint8_t* src = a.slices + (slot < 0 ? 0 : (size_t)slot * a.slice_pitch) + (size_t)y * Z + z0;
+        const int z = z0 + 2 * lane;
+        uint32_t q0 = 0, q1 = 0;
+        if (slot >= 0) {
+            if (even && z + 1 < Z) { const uint32_t u = __ldg(reinterpret_cast<const uint16_t*>(src) + lane); q0 = u & 0xff; q1 = u >> 8; }
+            else { if (z < Z) q0 = __ldg(src + 2 * lane); if (z + 1 < Z) q1 = __ldg(src + 2 * lane + 1); }
+        }
+        *reinterpret_cast<uint16_t*>(&tile[xr][2 * lane]) = (uint16_t)((q0 ? 1u : 0u) | (q1 ? 0x100u : 0u));
+    }
+    __syncthreads();
+    const bool even_out = (X & 1) == 0;
+    for (int zr = warp; zr < kTile; zr += 8) {
+        const int z = z0 + zr;
+        if (z >= Z) break;
+        const size_t off = (((size_t)v * Z + z) * Y + y) * X + x0;
+        const int xr = 2 * lane, x = x0 + xr;
+        const uint32_t b0 = tile[xr][zr], b1 = tile[xr + 1][zr];
+        if (a.vol_u8) {
+            if (even_out && x + 1 < X) *reinterpret_cast<uint16_t*>(a.vol_u8 + off + xr) = (uint16_t)(b0 | (b1 << 8));
+            else { if (x < X) a.vol_u8[off + xr] = (uint8_t)b0; if (x + 1 < X) a.vol_u8[off + xr + 1] = (uint8_t)b1; }
+        }
+        if (a.vol_f32) {
+            if (x < X) a.vol_f32[off + xr] = (float)b0;
+            if (x + 1 < X) a.vol_f32[off + xr + 1] = (float)b1;
         }
     }
 }
@@ -123,13 +174,45 @@ __device__ __forceinline__ uint32_t vote4(uint32_t a, uint32_t b, uint32_t c, in
 }
 
 struct Counts4 { int tp, fp, fn, tn; };
+// exact predicates of the reference (==1 / ==0 per byte); used for the rare words that hold a non-binary byte
 __device__ __forceinline__ void count4(Counts4& c, uint32_t g1, uint32_t g0, uint32_t p) {
     uint32_t p1 = one_bytes(p), p0 = zero_bytes(p);
     c.tp += __popc(g1 & p1); c.fp += __popc(g0 & p1);
     c.fn += __popc(g1 & p0); c.tn += __popc(g0 & p0);
 }
 
+// Binary words (every byte 0 or 1 - the only kind real masks contain) are counted with byte-lane SIMD adds on the
+// main ALU pipe: per plane only sum(g & p) and sum(p) are accumulated (+ one sum(g)); tp = sum(g&p),
+// fp = sum(p) - tp, fn = sum(g) - tp, tn = n - tp - fp - fn.  Byte lanes hold at most kFlush * 2 <= 254.
 constexpr int kCntThreads = 256;
+constexpr int kFlush = 120;
+
+template <int NPLANE>
+struct BinAcc {
+    uint32_t gp[NPLANE], p[NPLANE], g;
+    int s_gp[NPLANE], s_p[NPLANE], s_g, n;
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < NPLANE; ++i) { gp[i] = 0; p[i] = 0; s_gp[i] = 0; s_p[i] = 0; }
+        g = 0; s_g = 0; n = 0;
+    }
+    __device__ __forceinline__ void flush() {
+#pragma unroll
+        for (int i = 0; i < NPLANE; ++i) {
+            s_gp[i] = __dp4a(gp[i], 0x01010101u, (unsigned)s_gp[i]); gp[i] = 0;
+            s_p[i] = __dp4a(p[i], 0x01010101u, (unsigned)s_p[i]); p[i] = 0;
+        }
+        s_g = __dp4a(g, 0x01010101u, (unsigned)s_g); g = 0;
+    }
+    __device__ __forceinline__ void fold(Counts4 (&c)[NPLANE]) {
+        flush();
+#pragma unroll
+        for (int i = 0; i < NPLANE; ++i) {
+            const int tp = s_gp[i], fp = s_p[i] - tp, fn = s_g - tp;
+            c[i].tp += tp; c[i].fp += fp; c[i].fn += fn; c[i].tn += n - tp - fp - fn;
+        }
+    }
+};
 
 template <int NPLANE>
 __device__ __forceinline__ void flush_counts(Counts4 (&c)[NPLANE], long long* dst) {
@@ -156,6 +239,21 @@ struct VoteArgs {
     int umbral;
 };
 
+__device__ __forceinline__ void vote_count_word(uint32_t g, uint32_t a, uint32_t c, uint32_t s, uint32_t r,
+                                                BinAcc<4>& acc, Counts4 (&slow)[4]) {
+    if (((g | a | c | s) & 0xfefefefeu) == 0) {
+        acc.g += g;
+        acc.gp[0] += g & a; acc.p[0] += a;
+        acc.gp[1] += g & c; acc.p[1] += c;
+        acc.gp[2] += g & s; acc.p[2] += s;
+        acc.gp[3] += g & r; acc.p[3] += r;
+        acc.n += 4;
+    } else {
+        const uint32_t g1 = one_bytes(g), g0 = zero_bytes(g);
+        count4(slow[0], g1, g0, a); count4(slow[1], g1, g0, c); count4(slow[2], g1, g0, s); count4(slow[3], g1, g0, r);
+    }
+}
+
 // grid (chunks, nvol).  VEC: 8-byte granules (nvox % 8 == 0 and 8-byte aligned bases) or bytes.
 template <bool VEC>
 __global__ void __launch_bounds__(kCntThreads) consensus_eval_kernel(const VoteArgs a) {
@@ -170,20 +268,23 @@ __global__ void __launch_bounds__(kCntThreads) consensus_eval_kernel(const VoteA
         const uint2* sa = reinterpret_cast<const uint2*>(a.sa + off);
         const uint2* gt = cnt ? reinterpret_cast<const uint2*>(a.gt + off) : nullptr;
         uint2* out = a.consenso ? reinterpret_cast<uint2*>(a.consenso + off) : nullptr;
+        BinAcc<4> acc;
+        acc.init();
+        int it = 0;
         for (size_t g = (size_t)blockIdx.x * kCntThreads + threadIdx.x; g < ng; g += (size_t)gridDim.x * kCntThreads) {
-            uint2 wa = __ldg(ax + g), wc = __ldg(co + g), ws = __ldg(sa + g);
-            uint2 wg = cnt ? __ldg(gt + g) : make_uint2(0, 0);
+            const uint2 wa = __ldg(ax + g), wc = __ldg(co + g), ws = __ldg(sa + g);
+            const uint2 wg = cnt ? __ldg(gt + g) : make_uint2(0, 0);
             uint2 r;
             r.x = vote4(wa.x, wc.x, ws.x, a.umbral);
             r.y = vote4(wa.y, wc.y, ws.y, a.umbral);
             if (out) out[g] = r;
             if (cnt) {
-                uint32_t g1 = one_bytes(wg.x), g0 = zero_bytes(wg.x);
-                count4(c[0], g1, g0, wa.x); count4(c[1], g1, g0, wc.x); count4(c[2], g1, g0, ws.x); count4(c[3], g1, g0, r.x);
-                g1 = one_bytes(wg.y); g0 = zero_bytes(wg.y);
-                count4(c[0], g1, g0, wa.y); count4(c[1], g1, g0, wc.y); count4(c[2], g1, g0, ws.y); count4(c[3], g1, g0, r.y);
+                vote_count_word(wg.x, wa.x, wc.x, ws.x, r.x, acc, c);
+                vote_count_word(wg.y, wa.y, wc.y, ws.y, r.y, acc, c);
+                if (++it == kFlush) { acc.flush(); it = 0; }
             }
         }
+        if (cnt) acc.fold(c);
     } else {
         for (size_t i = (size_t)blockIdx.x * kCntThreads + threadIdx.x; i < a.nvox; i += (size_t)gridDim.x * kCntThreads) {
             uint32_t pa = a.ax[off + i], pc = a.co[off + i], ps = a.sa[off + i];
@@ -211,11 +312,20 @@ __global__ void __launch_bounds__(kCntThreads) confusion_counts_kernel(const uin
         const size_t ng = nvox / 8;
         const uint2* g8 = reinterpret_cast<const uint2*>(gt + off);
         const uint2* p8 = reinterpret_cast<const uint2*>(pred + off);
+        BinAcc<1> acc;
+        acc.init();
+        int it = 0;
+        auto word = [&](uint32_t g, uint32_t p) {
+            if (((g | p) & 0xfefefefeu) == 0) { acc.g += g; acc.gp[0] += g & p; acc.p[0] += p; acc.n += 4; }
+            else count4(c[0], one_bytes(g), zero_bytes(g), p);
+        };
         for (size_t g = (size_t)blockIdx.x * kCntThreads + threadIdx.x; g < ng; g += (size_t)gridDim.x * kCntThreads) {
-            uint2 wg = __ldg(g8 + g), wp = __ldg(p8 + g);
-            count4(c[0], one_bytes(wg.x), zero_bytes(wg.x), wp.x);
-            count4(c[0], one_bytes(wg.y), zero_bytes(wg.y), wp.y);
+            const uint2 wg = __ldg(g8 + g), wp = __ldg(p8 + g);
+            word(wg.x, wp.x);
+            word(wg.y, wp.y);
+            if (++it == kFlush) { acc.flush(); it = 0; }
         }
+        acc.fold(c);
     } else {
         for (size_t i = (size_t)blockIdx.x * kCntThreads + threadIdx.x; i < nvox; i += (size_t)gridDim.x * kCntThreads) {
             uint32_t g = gt[off + i] | 0x02020200u, p = pred[off + i] | 0x02020200u;
@@ -244,24 +354,43 @@ int launch_recon(const uint8_t* slices, size_t slice_pitch, const int32_t* vol_o
                  int32_t* slot_of, cudaStream_t stream) {
     const int n_plane = plano == MSL_AXIAL ? Z : (plano == MSL_CORONAL ? Y : X);
     const size_t nmap = (size_t)nvol * n_plane;
-    { ProfScope prof(K_RECON_FILL, stream);
-    fill_i32_kernel<<<(unsigned)((nmap + 255) / 256), 256, 0, stream>>>(slot_of, nmap, -1);
+    const size_t N = (size_t)nvol * X * Y * Z;
+    int32_t* xrange = slot_of + nmap;                     // [nvol][2] first / last present index
+    if (vol_u8) MSL_CUDA_CHECK(cudaMemsetAsync(vol_u8, 0, N, stream));
+    if (vol_f32) MSL_CUDA_CHECK(cudaMemsetAsync(vol_f32, 0, N * sizeof(float), stream));
+    if (nslices <= 0) return MSL_OK;
+    {
+        ProfScope prof(K_RECON_FILL, stream);
+        recon_init_kernel<<<(unsigned)((nmap + 255) / 256), 256, 0, stream>>>(slot_of, nmap, xrange, nvol);
     }
-    MSL_LAUNCH_CHECK("fill_i32_kernel");
-    if (nslices > 0) {
+    MSL_LAUNCH_CHECK("recon_init_kernel");
+    {
         ProfScope prof(K_RECON_SLOT_MAP, stream);
-        slot_map_kernel<<<(nslices + 255) / 256, 256, 0, stream>>>(vol_of_slice, idx_of_slice, nslices, nvol, n_plane, slot_of);
-        MSL_LAUNCH_CHECK("slot_map_kernel");
+        slot_map_kernel<<<(nslices + 255) / 256, 256, 0, stream>>>(vol_of_slice, idx_of_slice, nslices, nvol, n_plane, slot_of, xrange);
     }
+    MSL_LAUNCH_CHECK("slot_map_kernel");
     ReconArgs a;
-    a.slices = slices; a.slice_pitch = slice_pitch; a.slot_of = slot_of; a.vol_u8 = vol_u8; a.vol_f32 = vol_f32;
-    a.X = X; a.Y = Y; a.Z = Z; a.plano = plano;
-    const int W = plano == MSL_AXIAL ? Y : Z;
-    const int T = plano == MSL_AXIAL ? Z : Y;
-    dim3 grid(((X + kTile - 1) / kTile) * ((W + kTile - 1) / kTile), T, nvol);
+    a.slices = slices; a.slice_pitch = slice_pitch; a.vol_of_slice = vol_of_slice; a.idx_of_slice = idx_of_slice;
+    a.slot_of = slot_of; a.xrange = xrange; a.vol_u8 = vol_u8; a.vol_f32 = vol_f32;
+    a.X = X; a.Y = Y; a.Z = Z; a.plano = plano; a.nvol = nvol;
     ProfScope prof(K_RECON_GATHER, stream);
-    recon_gather_kernel<<<grid, 256, 0, stream>>>(a);
-    MSL_LAUNCH_CHECK("recon_gather_kernel");
+    if (plano == MSL_SAGITAL) {
+        dim3 grid(((X + kTile - 1) / kTile) * ((Z + kTile - 1) / kTile), Y, nvol);
+        recon_sagital_kernel<<<grid, 256, 0, stream>>>(a);
+    } else {
+        const int W = plano == MSL_AXIAL ? Y : Z;
+        const size_t smem = (size_t)W * ((X + 4) & ~1);
+        if (smem > 227 * 1024) { set_error("recon: a %d x %d slice does not fit shared memory", X, W); return MSL_ERR_UNSUPPORTED; }
+        const bool pair = ((X | W) & 1) == 0 && ((slice_pitch | reinterpret_cast<uintptr_t>(slices) | reinterpret_cast<uintptr_t>(vol_u8)) & 1) == 0;
+        if (pair) {
+            MSL_CUDA_CHECK(cudaFuncSetAttribute(recon_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            recon_rows_kernel<true><<<nslices, 256, smem, stream>>>(a);
+        } else {
+            MSL_CUDA_CHECK(cudaFuncSetAttribute(recon_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            recon_rows_kernel<false><<<nslices, 256, smem, stream>>>(a);
+        }
+    }
+    MSL_LAUNCH_CHECK("recon kernel");
     return MSL_OK;
 }
 
