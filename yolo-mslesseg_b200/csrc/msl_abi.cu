@@ -85,7 +85,7 @@ static size_t u_stack_bytes_per_volume(int X, int Y, int Z) {
 
 static int enhance_chunk_volumes(void) {
     const char* e = getenv("MSL_VOLUME_CHUNK");
-    int c = e ? atoi(e) : 4;
+    int c = e ? atoi(e) : 16;
     return c < 1 ? 1 : c;
 }
 
@@ -234,7 +234,7 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z, uint8_t
             clahe_geometry(rows, cols, p);
             const bool dense_ok = (npx % 4 == 0) && rows >= 2 && (align & 3) == 0 &&
                                   (unsigned long long)npx * (unsigned)rows < 0x100000000ull &&
-                                  2560 + (size_t)(rows + cols) * 16 + 65536 + dense_u_pitch(npx) <= 227 * 1024;
+                                  dense_smem_bytes(rows, cols, dst[MSL_MEJORA_CLAHE] != nullptr) <= 227 * 1024;
             if (dense_ok) {
                 rc = launch_enhance_dense(U[pl], upitch[pl], nv * n_p[pl], rows, cols, dst[MSL_MEJORA_HE], dst[MSL_MEJORA_CLAHE],
                                           dst[MSL_MEJORA_GC], dst[MSL_MEJORA_LT], tables, p.cl_th, p.cl_tw, p.cl_clip, p.cl_lut_scale, stream);
