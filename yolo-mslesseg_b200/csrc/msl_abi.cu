@@ -232,9 +232,7 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z, uint8_t
             EnhParams p;
             memset(&p, 0, sizeof(p));
             clahe_geometry(rows, cols, p);
-            const bool dense_ok = (npx % 4 == 0) && rows >= 2 && (align & 3) == 0 &&
-                                  (unsigned long long)npx * (unsigned)rows < 0x100000000ull &&
-                                  dense_smem_bytes(rows, cols, dst[MSL_MEJORA_CLAHE] != nullptr) <= 227 * 1024;
+            const bool dense_ok = dense_supported(rows, cols, dst[MSL_MEJORA_CLAHE] != nullptr) && (align & 3) == 0;
             if (dense_ok) {
                 rc = launch_enhance_dense(U[pl], upitch[pl], nv * n_p[pl], rows, cols, dst[MSL_MEJORA_HE], dst[MSL_MEJORA_CLAHE],
                                           dst[MSL_MEJORA_GC], dst[MSL_MEJORA_LT], tables, p.cl_th, p.cl_tw, p.cl_clip, p.cl_lut_scale, stream);

@@ -55,7 +55,8 @@ constexpr int kOffUstart = 512;    // u16[257] first u whose LUT_L[u] >= L     (
 constexpr int kOffT3 = 1040;       // u32[256] he | gc << 8 | lt << 16
 constexpr int kOffHeHist = 2064;   // u32[256]
 constexpr int kOffMisc = 3088;     // int[32]
-constexpr int kOffTabs = 3216;     // xw[cols] f32 | xo[cols] u32 | yw[rows] f32 | yo[rows] u32 | R (64 KB) | su[npx16]
+constexpr int kOffTabs = 3216;     // xw[cols] f32 | xo[cols] u32 | yw[rows] f32 | yo[rows] u32 | R | su[npx16]
+constexpr int kRBytes = 32768 + 2048;   // R: 64 tile slots of 512 B (histogram, then byte LUT) + the tile-index maps
 
 __device__ __forceinline__ unsigned add_hist16(unsigned* ht, int bin) {
     return atomicAdd(&ht[bin >> 1], 1u << ((bin & 1) * 16));
@@ -76,9 +77,10 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
     uint32_t* xo = reinterpret_cast<uint32_t*>(xw + (DO_CLAHE ? cols : 0));
     float* yw = reinterpret_cast<float*>(xo + (DO_CLAHE ? cols : 0));   // indexed by P column c (slice row a = c)
     uint32_t* yo = reinterpret_cast<uint32_t*>(yw + (DO_CLAHE ? rows : 0));
-    uint8_t* R = reinterpret_cast<uint8_t*>(yo + (DO_CLAHE ? rows : 0));
-    R = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(R) + 15) & ~(uintptr_t)15);
-    uint8_t* su = R + (DO_CLAHE ? 65536 : 0);
+    // (offsets, not pointer casts: an integer round trip would make the compiler fall back to generic LD/ST)
+    const int offR = (kOffTabs + (DO_CLAHE ? (rows + cols) * 8 : 0) + 15) & ~15;
+    uint8_t* R = smem + offR;
+    uint8_t* su = R + (DO_CLAHE ? kRBytes : 0);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t s = blockIdx.x;
@@ -120,15 +122,28 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
         for (int a = tid; a < rows; a += kThreads) tya[a] = (uint8_t)(a / th);
         for (int r = tid; r < cols; r += kThreads) txr[r] = (uint8_t)((cols - 1 - r) / tw);
         __syncthreads();
-        for (int q = tid; q < nw; q += kThreads) {
-            const unsigned o = 4u * q;
+        for (int q0 = warp * 32; q0 < nw; q0 += kThreads) {      // warp-uniform trip count: ballots inside
+            const int q = q0 + lane;
+            const bool live = q < nw;
+            const unsigned o = 4u * (live ? q : 0);
             int r = (int)__umulhi(o, p.magic_w);
             int c = (int)o - r * W;
-            const uint32_t w = su32[q];
-            if (c + 3 < W) {
-                const int tx = txr[r];
-                const int t0 = tya[c] * 8 + tx, t3i = tya[c + 3] * 8 + tx;
-                if (w == 0 && t0 == t3i) { atomicAdd(&hist[t0 * 128], 4u); continue; }
+            const uint32_t w = live ? su32[q] : 1u;
+            const bool inrow = c + 3 < W;
+            int t0 = 0, t3i = 0, tx = 0;
+            if (inrow) { tx = txr[r]; t0 = tya[c] * 8 + tx; t3i = tya[c + 3] * 8 + tx; }
+            // zero words inside one tile: neighbouring lanes all hit the same bin -> one atomic per warp and tile
+            const bool zw = live && inrow && w == 0 && t0 == t3i;
+            const unsigned zmask = __ballot_sync(FULL, zw);
+            if (zmask) {
+                const int leader = __ffs(zmask) - 1;
+                const int tl = __shfl_sync(FULL, t0, leader);
+                const unsigned same = __ballot_sync(FULL, zw && t0 == tl);
+                if (lane == leader) atomicAdd(&hist[tl * 128], 4u * __popc(same));
+                else if (zw && t0 != tl) atomicAdd(&hist[t0 * 128], 4u);
+            }
+            if (!live || zw) continue;
+            if (inrow) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int t = (k == 0) ? t0 : (k == 3 ? t3i : tya[c + k] * 8 + tx);
@@ -242,8 +257,11 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int L = lane * 8 + k;
+            const int u0 = ustart[L], n = (int)ustart[L + 1] - u0;   // cv2's LUT_L folds at most two grays into one L
             int acc = 0;
-            for (int u = ustart[L]; u < (int)ustart[L + 1]; ++u) acc += hu[u];
+            if (n > 0) acc = hu[u0];
+            if (n > 1) acc += hu[u0 + 1];
+            for (int u = u0 + 2; u < u0 + n; ++u) acc += hu[u];
             hb[k] = acc;
         }
         __syncwarp();
@@ -286,49 +304,57 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
             const float txf = __fsub_rn(__fmul_rn((float)b, inv_tw), 0.5f);
             const int t1 = (int)floorf(txf), t2 = t1 + 1;
             xw[r] = __fsub_rn(txf, (float)t1);
-            xo[r] = (uint32_t)(max(t1, 0) * 256) | ((uint32_t)(min(t2, 7) * 256) << 16);
+            xo[r] = (uint32_t)(max(t1, 0) * 512) | ((uint32_t)(min(t2, 7) * 512) << 16);
         }
         for (int a = tid; a < rows; a += kThreads) {
             const float tyf = __fsub_rn(__fmul_rn((float)a, inv_th), 0.5f);
             const int t1 = (int)floorf(tyf), t2 = t1 + 1;
             yw[a] = __fsub_rn(tyf, (float)t1);
-            yo[a] = (uint32_t)(max(t1, 0) * 2048) | ((uint32_t)(min(t2, 7) * 2048) << 16);
+            yo[a] = (uint32_t)(max(t1, 0) * 4096) | ((uint32_t)(min(t2, 7) * 4096) << 16);
         }
     }
     __syncthreads();
-    // compose with LUT_L and widen to float: F[t][u] = (float) T[t][LUT_L[u]]  (64 KB overlaying the histograms)
-    float* F = reinterpret_cast<float*>(R);
+    // compose with LUT_L in place: B[t][u] = T[t][LUT_L[u]]  (256 bytes at the head of every tile's 512-byte slot).
+    // Byte tables keep four neighbouring grays in one 32-bit word, so a warp's random lookups collide at most 2-way.
     {
-        float fv[4][8];
+        uint32_t bv[4][2];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint8_t* T = R + (warp + j * kWarps) * 512;
+            uint32_t lo = 0, hi = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) fv[j][k] = (float)T[lutl[lane * 8 + k]];
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t v = T[lutl[lane * 8 + k]];
+                if (k < 4) lo |= v << (8 * k); else hi |= v << (8 * (k - 4));
+            }
+            bv[j][0] = lo; bv[j][1] = hi;
         }
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float4* dst = reinterpret_cast<float4*>(F + (warp + j * kWarps) * 256 + lane * 8);
-            dst[0] = make_float4(fv[j][0], fv[j][1], fv[j][2], fv[j][3]);
-            dst[1] = make_float4(fv[j][4], fv[j][5], fv[j][6], fv[j][7]);
-        }
+        for (int j = 0; j < 4; ++j)
+            reinterpret_cast<uint2*>(R + (warp + j * kWarps) * 512)[lane] = make_uint2(bv[j][0], bv[j][1]);
     }
     __syncthreads();
 
     // ---------------------------------------------------------------- CLAHE: bilinear blend + LUT_OUT, in place
-    // Consecutive lanes take consecutive pixels (conflict-free table reads); the result byte replaces u in smem.
+    // Consecutive lanes take consecutive pixels (conflict-free weight / offset reads); tile offsets are byte offsets
+    // into R; the result byte replaces u in smem and the slice is then copied out with 32-bit stores.
     for (int o = tid; o < npx; o += kThreads) {
         const int r = (int)__umulhi((unsigned)o, p.magic_w);
         const int c = o - r * W;
         const float xa = xw[r], xa1 = __fsub_rn(1.0f, xa);
         const float ya = yw[c], ya1 = __fsub_rn(1.0f, ya);
-        const uint32_t xoff = xo[r], yoff = yo[c];
-        const float* F1 = F + (yoff & 0xffff) + su[o];
-        const float* F2 = F + (yoff >> 16) + su[o];
+        const uint32_t xoff = xo[r], yoff = yo[c], v = su[o];
+        const uint8_t* B1 = R + (yoff & 0xffff) + v;
+        const uint8_t* B2 = R + (yoff >> 16) + v;
         const int x1 = xoff & 0xffff, x2 = xoff >> 16;
-        const float top = __fadd_rn(__fmul_rn(F1[x1], xa1), __fmul_rn(F1[x2], xa));
-        const float bot = __fadd_rn(__fmul_rn(F2[x1], xa1), __fmul_rn(F2[x2], xa));
+        // uint8 -> float without the conversion pipe: bits(2^23 + b) - 2^23
+        const float l11 = __fsub_rn(__uint_as_float(0x4b000000u | B1[x1]), 8388608.0f);
+        const float l12 = __fsub_rn(__uint_as_float(0x4b000000u | B1[x2]), 8388608.0f);
+        const float l21 = __fsub_rn(__uint_as_float(0x4b000000u | B2[x1]), 8388608.0f);
+        const float l22 = __fsub_rn(__uint_as_float(0x4b000000u | B2[x2]), 8388608.0f);
+        const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+        const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
         const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
         // cvRound (half-even) of a value in [0, 255.0001]: the low mantissa bits of res + 1.5 * 2^23
         su[o] = lutout[__float_as_uint(__fadd_rn(res, 12582912.0f)) & 0xffu];
@@ -347,7 +373,13 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
 size_t dense_u_pitch(int npx) { return ((size_t)npx + 15) & ~(size_t)15; }
 
 size_t dense_smem_bytes(int rows, int cols, bool clahe) {
-    return (size_t)kOffTabs + (clahe ? (size_t)(rows + cols) * 8 + 65536 : 0) + 16 + dense_u_pitch(rows * cols);
+    return (size_t)kOffTabs + (clahe ? (size_t)(rows + cols) * 8 + kRBytes : 0) + 16 + dense_u_pitch(rows * cols);
+}
+
+bool dense_supported(int rows, int cols, bool clahe) {
+    const long long npx = (long long)rows * cols;
+    return (npx % 4 == 0) && rows >= 2 && npx * rows < 0x100000000ll && rows + cols + 8 <= 2048 &&
+           dense_smem_bytes(rows, cols, clahe) <= 227 * 1024;
 }
 
 int launch_enhance_dense(const uint8_t* U, size_t u_pitch, int nslices, int rows, int cols,
@@ -361,10 +393,9 @@ int launch_enhance_dense(const uint8_t* U, size_t u_pitch, int nslices, int rows
     p.magic_w = (unsigned)(0x100000000ull / (unsigned)rows) + 1u;
     const bool cl = out_clahe != nullptr;
     const size_t smem = dense_smem_bytes(rows, cols, cl);
-    if (smem > 227 * 1024 || (u_pitch & 15) || (reinterpret_cast<uintptr_t>(U) & 15) ||
+    if (!dense_supported(rows, cols, cl) || (u_pitch & 15) || (reinterpret_cast<uintptr_t>(U) & 15) ||
         ((reinterpret_cast<uintptr_t>(out_he) | reinterpret_cast<uintptr_t>(out_clahe) | reinterpret_cast<uintptr_t>(out_gc) |
-          reinterpret_cast<uintptr_t>(out_lt)) & 3) || (npx & 3) || rows < 2 ||
-        (unsigned long long)npx * (unsigned)rows >= 0x100000000ull) {
+          reinterpret_cast<uintptr_t>(out_lt)) & 3)) {
         set_error("enhance_dense: unsupported geometry / alignment (%d x %d, %zu B smem)", rows, cols, smem);
         return MSL_ERR_UNSUPPORTED;
     }

@@ -83,6 +83,7 @@ int launch_norm_scatter(const float* vol, int nvol, int X, int Y, int Z, const u
 // Dense HE / CLAHE over PNG-oriented uint8 stacks (msl_enhance_dense.cu)
 size_t dense_u_pitch(int npx);
 size_t dense_smem_bytes(int rows, int cols, bool clahe);
+bool dense_supported(int rows, int cols, bool clahe);
 int launch_enhance_dense(const uint8_t* U, size_t u_pitch, int nslices, int rows, int cols,
                          uint8_t* out_he, uint8_t* out_clahe, uint8_t* out_gc, uint8_t* out_lt, const uint8_t* tables,
                          int th, int tw, int clip, float lut_scale, cudaStream_t stream);
