@@ -109,9 +109,10 @@ int msl_lesion_slices(const void* gt, int dtype, int nvol, int X, int Y, int Z,
  * idx_of_slice[s] (device int32 arrays; both NULL = dense: every index of every volume,
  * s = v * n_plane + i, and nslices must equal nvol * n_plane).  Entries outside the volume are
  * skipped.  Output slice s starts at out + s * slice_pitch_bytes.
- * Supported: mejora HE/CLAHE/GC/LT with any layout; mejora NONE with dtype U8 and any layout
- * (mask slices) or dtype F32 and a PNG layout (imsave of the raw slice, float64 normalisation).
- * MSL_F32 input is normalised per slice exactly like normalizar_a_uint8; MSL_U8 input is used as is. */
+ * MSL_F32 input is normalised per slice exactly like normalizar_a_uint8 (utils/utils.py:396-406); MSL_U8
+ * input is used as is.  mejora NONE: layouts G / P return that uint8 slice itself (the E1 output; mask
+ * slices for U8 input); the PNG layouts on F32 input reproduce imsave of the RAW slice (float64
+ * normalisation, what guardar_cortes saves when the experiment has no enhancement). */
 int msl_enhance_slices(const void* vol, int dtype, int nvol, int X, int Y, int Z,
                        int mejora, int plano,
                        const int32_t* vol_of_slice, const int32_t* idx_of_slice, int nslices,

@@ -45,8 +45,8 @@ def test_argument_errors_without_gpu():
     assert rc == _lib.ERR_ARG and b"NULL" in lib.msl_last_error()
     rc = lib.msl_enhance_images(ctypes.c_void_p(16), 0, 1, 8, 8, 64, 9, ctypes.c_void_p(16), 64, 0, ctypes.c_void_p(16), None)
     assert rc == _lib.ERR_ARG and b"mejora" in lib.msl_last_error()
-    rc = lib.msl_enhance_images(ctypes.c_void_p(16), 0, 1, 8, 8, 64, 0, ctypes.c_void_p(16), 64, 0, ctypes.c_void_p(16), None)
-    assert rc == _lib.ERR_UNSUPPORTED
+    rc = lib.msl_enhance_images(ctypes.c_void_p(16), 0, 1, 8, 8, 32, 0, ctypes.c_void_p(16), 64, 0, ctypes.c_void_p(16), None)
+    assert rc == _lib.ERR_ARG and b"pitch" in lib.msl_last_error()
     assert lib.msl_workspace_bytes(_lib.WS_RECON, 2, 182, 218, 182) == 2 * (218 + 2) * 4
     assert lib.msl_workspace_bytes(_lib.WS_ENHANCE_VOLUMES, 1, 182, 218, 182) > 3 * 7221032
     with pytest.raises(_lib.MslError):

@@ -50,10 +50,6 @@ int check_enhance_combo(int mejora, int dtype, int layout) {
     MSL_REQUIRE(mejora >= MSL_MEJORA_NONE && mejora <= MSL_MEJORA_LT, "mejora %d no reconocida", mejora);
     MSL_REQUIRE(dtype == MSL_F32 || dtype == MSL_U8, "dtype %d not in {MSL_F32, MSL_U8}", dtype);
     MSL_REQUIRE(layout >= MSL_OUT_G && layout <= MSL_OUT_PNG_RGBA, "layout %d not in MSL_OUT_*", layout);
-    if (mejora == MSL_MEJORA_NONE && dtype == MSL_F32 && layout < MSL_OUT_PNG_GRAY) {
-        set_error("mejora NONE on float input is only defined for the PNG layouts (the raw slice has no uint8 form)");
-        return MSL_ERR_UNSUPPORTED;
-    }
     return MSL_OK;
 }
 

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kThreads) enhance_slices_kernel(const EnhParam
         block_minmax(mn, mx, misc);
     }
 
-    if (p.mejora == MSL_MEJORA_NONE && sizeof(InT) == 4) {
+    if (p.mejora == MSL_MEJORA_NONE && sizeof(InT) == 4 && png) {
         // imsave of the raw float slice: float64 normalisation straight from global memory
         // (scripts/extraer_dataset.py:192 with mejora=None; matplotlib Normalize on float64 input).
         __syncthreads();

@@ -22,7 +22,7 @@ from . import tables as T
 PLANOS = ("axial", "coronal", "sagital")
 MEJORAS = ("HE", "CLAHE", "GC", "LT")
 _LAYOUT_ID = {"G": L.OUT_G, "P": L.OUT_P, "PNG_GRAY": L.OUT_PNG_GRAY, "PNG_RGBA": L.OUT_PNG_RGBA}
-_tables_cache: Dict[int, torch.Tensor] = {}
+_tables_cache: Dict[tuple, torch.Tensor] = {}
 
 
 def _stream() -> C.c_void_p:
@@ -48,13 +48,14 @@ def _dtype_id(t: torch.Tensor, name: str) -> int:
     raise TypeError(f"{name} must be float32 or uint8, got {t.dtype}")
 
 
-def device_tables(device) -> torch.Tensor:
-    """The MSL_TABLES_BYTES constant block, uploaded once per device."""
+def device_tables(device, lut_out: str = "gray") -> torch.Tensor:
+    """The MSL_TABLES_BYTES constant block, uploaded once per device (and per CLAHE output table, see
+    tables.host_tables)."""
     dev = torch.device(device)
-    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), lut_out)
     t = _tables_cache.get(key)
     if t is None:
-        t = torch.from_numpy(T.host_tables().copy()).to(dev)
+        t = torch.from_numpy(T.host_tables(lut_out).copy()).to(dev)
         _tables_cache[key] = t
     return t
 
@@ -103,7 +104,7 @@ def lesion_slices(gt: torch.Tensor):
 
 # ------------------------------------------------------------------------------------ E1-E8
 def enhance_slices(vol: torch.Tensor, mejora: Optional[str], plano: str, vol_of_slice=None, idx_of_slice=None,
-                   layout: str = "G", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   layout: str = "G", out: Optional[torch.Tensor] = None, lut_out: str = "gray") -> torch.Tensor:
     """Enhanced slices of resident volumes.  vol: [nvol, Z, Y, X] float32 (normalised per slice like
     normalizar_a_uint8) or uint8 (used as is).  With no index lists every slice of every volume is
     produced (s = v * n_plane + i)."""
@@ -135,11 +136,11 @@ def enhance_slices(vol: torch.Tensor, mejora: Optional[str], plano: str, vol_of_
     pitch = rows * cols * (4 if layout == "PNG_RGBA" else 1)
     L.check(L.load().msl_enhance_slices(
         _ptr(vol), _dtype_id(vol, "vol"), nvol, X, Y, Z, L.MEJORA_ID[mejora], L.PLANO_ID[plano],
-        _ptr(vs), _ptr(ix), ns, _ptr(out), pitch, _LAYOUT_ID[layout], _ptr(device_tables(vol.device)), _stream()))
+        _ptr(vs), _ptr(ix), ns, _ptr(out), pitch, _LAYOUT_ID[layout], _ptr(device_tables(vol.device, lut_out)), _stream()))
     return out
 
 
-def enhance_images(imgs: torch.Tensor, mejora: Optional[str], layout: str = "G") -> torch.Tensor:
+def enhance_images(imgs: torch.Tensor, mejora: Optional[str], layout: str = "G", lut_out: str = "gray") -> torch.Tensor:
     """Batch of C-contiguous 2-D images [n, rows, cols] (float32 or uint8) -> enhanced gray images."""
     _need_cuda(imgs, "imgs")
     if imgs.dim() != 3:
@@ -151,7 +152,7 @@ def enhance_images(imgs: torch.Tensor, mejora: Optional[str], layout: str = "G")
     pitch = rows * cols * (4 if layout == "PNG_RGBA" else 1)
     L.check(L.load().msl_enhance_images(
         _ptr(imgs), _dtype_id(imgs, "imgs"), n, rows, cols, rows * cols, L.MEJORA_ID[mejora],
-        _ptr(out), pitch, _LAYOUT_ID[layout], _ptr(device_tables(imgs.device)), _stream()))
+        _ptr(out), pitch, _LAYOUT_ID[layout], _ptr(device_tables(imgs.device, lut_out)), _stream()))
     return out
 
 
