@@ -148,7 +148,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -342,7 +342,7 @@ def run_ours(args):
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "stages": stages, "kernels": kernels, "verified": verified,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -470,8 +470,25 @@ def run_e2e(args, torch, dist, ops, S, device, world, flair, gt, preds):
             "ms_per_step": sec * 1e3, "steps": K, "note": "pinned host buffers, 4-volume chunks over 3 streams; wall clock around synchronised steps"}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter) was
+    redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # fd 1 -> stderr for the rest of the run
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
