@@ -95,14 +95,66 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
         for (int q = tid; q < 32768 / 16; q += kThreads) r4[q] = make_uint4(0, 0, 0, 0);
     }
     // ---------------------------------------------------------------- load
+    uint32_t anynz = 0;
     {
         const int nvec = npx >> 4;
         const uint4* in4 = reinterpret_cast<const uint4*>(in);
         uint4* su4 = reinterpret_cast<uint4*>(su);
-        for (int q = tid; q < nvec; q += kThreads) su4[q] = __ldg(in4 + q);
-        for (int o = (nvec << 4) + tid; o < npx; o += kThreads) su[o] = __ldg(in + o);
+        for (int q = tid; q < nvec; q += kThreads) { const uint4 v = __ldg(in4 + q); su4[q] = v; anynz |= v.x | v.y | v.z | v.w; }
+        for (int o = (nvec << 4) + tid; o < npx; o += kThreads) { const uint32_t b = __ldg(in + o); su[o] = (uint8_t)b; anynz |= b; }
     }
-    __syncthreads();
+    // Blank slice (the skull-stripped volumes have ~15 % of them per plane): every output is a constant.
+    // HE: one populated bin -> that bin's index (0); GC_T[0]; LT_T[.][0]; CLAHE: all 64 tiles are identical, their
+    // histogram is {0: tile area}, so the generic clip / redistribute / CDF below is run for ONE tile by warp 0.
+    if (!__syncthreads_or(anynz != 0)) {
+        uint32_t c_he = 0, c_gc = __ldg(p.tables + MSL_TAB_GC), c_lt = __ldg(p.tables + MSL_TAB_LT + 255 * 256), c_cl = 0;
+        if (DO_CLAHE) {
+            if (warp == 0) {
+                const int area = p.th * p.tw, clip = p.clip;
+                // L = LUT_L[0] holds the whole tile
+                const int L0 = lutl[0];
+                int hb[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) hb[k] = (lane * 8 + k == L0) ? area : 0;
+                int clipped = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (hb[k] > clip) { clipped += hb[k] - clip; hb[k] = clip; }
+                clipped = warp_sum(clipped);
+                const int rb = clipped / 256, res = clipped - rb * 256;
+                const int step = res > 0 ? max(256 / res, 1) : 256;
+                int run = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int bin = lane * 8 + k;
+                    hb[k] += rb;
+                    if (res > 0 && (bin % step) == 0 && (bin / step) < res) hb[k] += 1;
+                    run += hb[k];
+                    hb[k] = run;
+                }
+                const int excl = warp_incl_scan(run, lane) - run;
+                // the blend of four equal tile values z is z after rounding; the pixel value is T[LUT_L[0]]
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (lane * 8 + k == L0) misc[20] = lutout[sat_u8_rn(__fmul_rn((float)(hb[k] + excl), p.lut_scale))];
+            }
+            __syncthreads();
+            c_cl = (uint32_t)misc[20];
+        }
+        uint8_t* outs[4] = {p.out_he, p.out_clahe, p.out_gc, p.out_lt};
+        const uint32_t cv[4] = {c_he, c_cl, c_gc, c_lt};
+        const int nw0 = npx >> 2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (!outs[j]) continue;
+            uint8_t* out = outs[j] + s * p.out_pitch;
+            uint32_t* out32 = reinterpret_cast<uint32_t*>(out);
+            const uint32_t w4 = cv[j] * 0x01010101u;
+            for (int q = tid; q < nw0; q += kThreads) out32[q] = w4;
+            for (int o = (nw0 << 2) + tid; o < npx; o += kThreads) out[o] = (uint8_t)cv[j];
+        }
+        return;
+    }
 
     const int th = p.th, tw = p.tw;
     unsigned* hist = reinterpret_cast<unsigned*>(R);        // 64 tiles x 128 words (two 16-bit bins per word)
