@@ -271,17 +271,30 @@ __global__ void __launch_bounds__(kCntThreads) consensus_eval_kernel(const VoteA
         BinAcc<4> acc;
         acc.init();
         int it = 0;
-        for (size_t g = (size_t)blockIdx.x * kCntThreads + threadIdx.x; g < ng; g += (size_t)gridDim.x * kCntThreads) {
+        // two granules per iteration: eight independent 64-bit loads in flight per thread
+        const size_t stride = (size_t)gridDim.x * kCntThreads;
+        for (size_t g = (size_t)blockIdx.x * kCntThreads + threadIdx.x; g < ng; g += 2 * stride) {
+            const size_t g2 = g + stride;
+            const bool has2 = g2 < ng;
+            const size_t gb = has2 ? g2 : g;
             const uint2 wa = __ldg(ax + g), wc = __ldg(co + g), ws = __ldg(sa + g);
+            const uint2 xa = __ldg(ax + gb), xc = __ldg(co + gb), xs = __ldg(sa + gb);
             const uint2 wg = cnt ? __ldg(gt + g) : make_uint2(0, 0);
-            uint2 r;
+            const uint2 xg = cnt ? __ldg(gt + gb) : make_uint2(0, 0);
+            uint2 r, r2;
             r.x = vote4(wa.x, wc.x, ws.x, a.umbral);
             r.y = vote4(wa.y, wc.y, ws.y, a.umbral);
-            if (out) out[g] = r;
+            r2.x = vote4(xa.x, xc.x, xs.x, a.umbral);
+            r2.y = vote4(xa.y, xc.y, xs.y, a.umbral);
+            if (out) { out[g] = r; if (has2) out[g2] = r2; }
             if (cnt) {
                 vote_count_word(wg.x, wa.x, wc.x, ws.x, r.x, acc, c);
                 vote_count_word(wg.y, wa.y, wc.y, ws.y, r.y, acc, c);
-                if (++it == kFlush) { acc.flush(); it = 0; }
+                if (has2) {
+                    vote_count_word(xg.x, xa.x, xc.x, xs.x, r2.x, acc, c);
+                    vote_count_word(xg.y, xa.y, xc.y, xs.y, r2.y, acc, c);
+                }
+                if (++it == kFlush / 2) { acc.flush(); it = 0; }
             }
         }
         if (cnt) acc.fold(c);
