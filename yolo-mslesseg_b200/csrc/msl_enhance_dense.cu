@@ -56,7 +56,9 @@ constexpr int kOffT3 = 1040;       // u32[256] he | gc << 8 | lt << 16
 constexpr int kOffHeHist = 2064;   // u32[256]
 constexpr int kOffMisc = 3088;     // int[32]
 constexpr int kOffTabs = 3216;     // xw[cols] f32 | xo[cols] u32 | yw[rows] f32 | yo[rows] u32 | R | su[npx16]
-constexpr int kRBytes = 32768 + 2048;   // R: 64 tile slots of 512 B (histogram, then byte LUT) + the tile-index maps
+constexpr int kPairTy = 256 * 20;          // bytes of pair tables per tile row: 256 grays x (9 pairs x 2 B, padded to 20)
+constexpr int kPairBytes = 8 * kPairTy;    // 40,960
+constexpr int kRBytes = kPairBytes + 64 * 256;   // R: tile histograms (first 32 KB) / pair tables (40 KB) + compacted tile LUTs (16 KB)
 
 __device__ __forceinline__ unsigned add_hist16(unsigned* ht, int bin) {
     return atomicAdd(&ht[bin >> 1], 1u << ((bin & 1) * 16));
@@ -346,70 +348,83 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
             uint32_t o = sat_u8_rn(__fmul_rn((float)(hb[k] + excl), p.lut_scale));
             if (k < 4) lo |= o << (8 * k); else hi |= o << (8 * (k - 4));
         }
-        reinterpret_cast<uint2*>(hist + t * 128)[lane] = make_uint2(lo, hi);      // T[t][L], 256 bytes at the head of the tile's slot
+        reinterpret_cast<uint2*>(R + kPairBytes + t * 256)[lane] = make_uint2(lo, hi);      // T[t][L], compact, behind the pair area
     }
-    // interpolation tables (OpenCV CLAHE_Interpolation_Body): blend weight + the two tile offsets per column / row
+    // interpolation tables (OpenCV CLAHE_Interpolation_Body): blend weight + table offsets per P row / P column.
+    //   P row r    (slice column b): weight xa, pair slot j = floor(txf) + 1 in [0, 8]  -> byte offset 2*j
+    //   P column c (slice row a)   : weight ya, tile rows ty1 / ty2                      -> byte offsets ty * kPairTy
     {
         const float inv_tw = __fdiv_rn(1.0f, (float)tw), inv_th = __fdiv_rn(1.0f, (float)th);
         for (int r = tid; r < cols; r += kThreads) {
             const int b = cols - 1 - r;
             const float txf = __fsub_rn(__fmul_rn((float)b, inv_tw), 0.5f);
-            const int t1 = (int)floorf(txf), t2 = t1 + 1;
+            const int t1 = (int)floorf(txf);
             xw[r] = __fsub_rn(txf, (float)t1);
-            xo[r] = (uint32_t)(max(t1, 0) * 512) | ((uint32_t)(min(t2, 7) * 512) << 16);
+            xo[r] = (uint32_t)(2 * (min(max(t1, -1), 7) + 1));
         }
         for (int a = tid; a < rows; a += kThreads) {
             const float tyf = __fsub_rn(__fmul_rn((float)a, inv_th), 0.5f);
             const int t1 = (int)floorf(tyf), t2 = t1 + 1;
             yw[a] = __fsub_rn(tyf, (float)t1);
-            yo[a] = (uint32_t)(max(t1, 0) * 4096) | ((uint32_t)(min(t2, 7) * 4096) << 16);
+            yo[a] = (uint32_t)(max(t1, 0) * kPairTy) | ((uint32_t)(min(t2, 7) * kPairTy) << 16);
         }
     }
     __syncthreads();
-    // compose with LUT_L in place: B[t][u] = T[t][LUT_L[u]]  (256 bytes at the head of every tile's 512-byte slot).
-    // Byte tables keep four neighbouring grays in one 32-bit word, so a warp's random lookups collide at most 2-way.
+    // Pair tables: PT[ty][u][j] = (T[ty][tx1][LUT_L[u]], T[ty][tx2][LUT_L[u]]) as one 16-bit entry for the nine
+    // horizontal neighbour pairs (tx1, tx2) = (0,0), (0,1), ..., (6,7), (7,7).  One 16-bit read fetches both operands
+    // of a horizontal blend; a gray level's nine entries take 20 bytes (5 words: odd stride -> spread over the banks).
+    // Thread = one gray level u and four tile rows: 8 byte reads (neighbouring u -> neighbouring L: conflict-free)
+    // and five 32-bit stores per tile row.
     {
-        uint32_t bv[4][2];
+        const uint8_t* Tc = R + kPairBytes;                  // [64][256]
+        const int uv = tid & 255, L = lutl[uv];
+        for (int ty = tid >> 8; ty < 8; ty += kThreads / 256) {
+            uint32_t t[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint8_t* T = R + (warp + j * kWarps) * 512;
-            uint32_t lo = 0, hi = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint32_t v = T[lutl[lane * 8 + k]];
-                if (k < 4) lo |= v << (8 * k); else hi |= v << (8 * (k - 4));
-            }
-            bv[j][0] = lo; bv[j][1] = hi;
+            for (int tx = 0; tx < 8; ++tx) t[tx] = Tc[(ty * 8 + tx) * 256 + L];
+            uint32_t* dst = reinterpret_cast<uint32_t*>(R + ty * kPairTy + uv * 20);
+            // pairs j = 0..8: (t0,t0) (t0,t1) (t1,t2) ... (t6,t7) (t7,t7), two 16-bit pairs per word
+            dst[0] = (t[0] | (t[0] << 8)) | ((t[0] | (t[1] << 8)) << 16);
+            dst[1] = (t[1] | (t[2] << 8)) | ((t[2] | (t[3] << 8)) << 16);
+            dst[2] = (t[3] | (t[4] << 8)) | ((t[4] | (t[5] << 8)) << 16);
+            dst[3] = (t[5] | (t[6] << 8)) | ((t[6] | (t[7] << 8)) << 16);
+            dst[4] = (t[7] | (t[7] << 8));
         }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            reinterpret_cast<uint2*>(R + (warp + j * kWarps) * 512)[lane] = make_uint2(bv[j][0], bv[j][1]);
     }
     __syncthreads();
 
     // ---------------------------------------------------------------- CLAHE: bilinear blend + LUT_OUT, in place
-    // Consecutive lanes take consecutive pixels (conflict-free weight / offset reads); tile offsets are byte offsets
-    // into R; the result byte replaces u in smem and the slice is then copied out with 32-bit stores.
-    for (int o = tid; o < npx; o += kThreads) {
-        const int r = (int)__umulhi((unsigned)o, p.magic_w);
-        const int c = o - r * W;
-        const float xa = xw[r], xa1 = __fsub_rn(1.0f, xa);
-        const float ya = yw[c], ya1 = __fsub_rn(1.0f, ya);
-        const uint32_t xoff = xo[r], yoff = yo[c], v = su[o];
-        const uint8_t* B1 = R + (yoff & 0xffff) + v;
-        const uint8_t* B2 = R + (yoff >> 16) + v;
-        const int x1 = xoff & 0xffff, x2 = xoff >> 16;
-        // uint8 -> float without the conversion pipe: bits(2^23 + b) - 2^23
-        const float l11 = __fsub_rn(__uint_as_float(0x4b000000u | B1[x1]), 8388608.0f);
-        const float l12 = __fsub_rn(__uint_as_float(0x4b000000u | B1[x2]), 8388608.0f);
-        const float l21 = __fsub_rn(__uint_as_float(0x4b000000u | B2[x1]), 8388608.0f);
-        const float l22 = __fsub_rn(__uint_as_float(0x4b000000u | B2[x2]), 8388608.0f);
-        const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
-        const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
-        const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
-        // cvRound (half-even) of a value in [0, 255.0001]: the low mantissa bits of res + 1.5 * 2^23
-        su[o] = lutout[__float_as_uint(__fadd_rn(res, 12582912.0f)) & 0xffu];
+    // A warp owns 32 consecutive P columns (slice rows) over a band of P rows: the vertical weight / offsets stay in
+    // registers, the horizontal ones are warp-uniform reads, pixel reads and writes are conflict-free.
+    {
+        const int nchunk = (W + 31) >> 5;
+        const int nband = 8, band_rows = (cols + nband - 1) / nband;
+        for (int task = warp; task < nchunk * nband; task += kWarps) {
+            const int cc = task % nchunk, band = task / nchunk;
+            const int c = cc * 32 + lane;
+            if (c >= W) continue;
+            const float ya = yw[c], ya1 = __fsub_rn(1.0f, ya);
+            const uint32_t yoff = yo[c];
+            const uint8_t* P1 = R + (yoff & 0xffff);
+            const uint8_t* P2 = R + (yoff >> 16);
+            const int r_end = min(cols, (band + 1) * band_rows);
+            for (int r = band * band_rows; r < r_end; ++r) {
+                const float xa = xw[r], xa1 = __fsub_rn(1.0f, xa);
+                const uint32_t off = 20u * su[r * W + c] + xo[r];
+                const uint32_t h1 = *reinterpret_cast<const uint16_t*>(P1 + off);
+                const uint32_t h2 = *reinterpret_cast<const uint16_t*>(P2 + off);
+                // uint8 -> float without the conversion pipe: bits(2^23 + b) - 2^23
+                const float l11 = __fsub_rn(__uint_as_float(0x4b000000u | (h1 & 0xff)), 8388608.0f);
+                const float l12 = __fsub_rn(__uint_as_float(0x4b000000u | (h1 >> 8)), 8388608.0f);
+                const float l21 = __fsub_rn(__uint_as_float(0x4b000000u | (h2 & 0xff)), 8388608.0f);
+                const float l22 = __fsub_rn(__uint_as_float(0x4b000000u | (h2 >> 8)), 8388608.0f);
+                const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+                const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+                const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+                // cvRound (half-even) of a value in [0, 255.0001]: the low mantissa bits of res + 1.5 * 2^23
+                su[r * W + c] = lutout[__float_as_uint(__fadd_rn(res, 12582912.0f)) & 0xffu];
+            }
+        }
     }
     __syncthreads();
     {
