@@ -24,7 +24,7 @@ namespace msl {
 
 namespace {
 
-constexpr int kThreads = 512;
+constexpr int kThreads = 768;
 constexpr int kWarps = kThreads / 32;
 
 struct DenseParams {

@@ -104,47 +104,48 @@ __global__ void __launch_bounds__(256) recon_rows_kernel(const ReconArgs a) {
 constexpr int kTile = 64;
 constexpr int kTilePitch = 68;     // 17 words: conflict-free column reads
 
-// grid (tiles_x * tiles_z, Y, nvol); block 256.
+// grid (tiles_z, Y, nvol); block 256.  Each CTA walks the x-tiles that overlap [first, last] present slice.
 __global__ void __launch_bounds__(256) recon_sagital_kernel(const ReconArgs a) {
     __shared__ __align__(4) uint8_t tile[kTile][kTilePitch];
     const int X = a.X, Y = a.Y, Z = a.Z;
-    const int tiles_x = (X + kTile - 1) / kTile;
-    const int tx = blockIdx.x % tiles_x, tz = blockIdx.x / tiles_x;
-    const int x0 = tx * kTile, z0 = tz * kTile;
+    const int z0 = blockIdx.x * kTile;
     const int y = blockIdx.y, v = blockIdx.z;
     const int xmin = a.xrange[2 * v], xmax = a.xrange[2 * v + 1];
-    if (xmax < x0 || xmin >= x0 + kTile) return;          // no present slice in this tile: the memset already wrote it
+    if (xmax < 0) return;                                 // this volume has no slice at all
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int32_t* slot_v = a.slot_of + (size_t)v * X;
     const bool even = ((a.slice_pitch | (size_t)Z | reinterpret_cast<uintptr_t>(a.slices)) & 1) == 0;
-    for (int xr = warp; xr < kTile; xr += 8) {
-        const int x = x0 + xr;
-        const int slot = x < X ? slot_v[x] : -1;
-        const uint8_t* src = a.slices + (slot < 0 ? 0 : (size_t)slot * a.slice_pitch) + (size_t)y * Z + z0;
-        const int z = z0 + 2 * lane;
-        uint32_t q0 = 0, q1 = 0;
-        if (slot >= 0) {
-            if (even && z + 1 < Z) { const uint32_t u = __ldg(reinterpret_cast<const uint16_t*>(src) + lane); q0 = u & 0xff; q1 = u >> 8; }
-            else { if (z < Z) q0 = __ldg(src + 2 * lane); if (z + 1 < Z) q1 = __ldg(src + 2 * lane + 1); }
-        }
-        *reinterpret_cast<uint16_t*>(&tile[xr][2 * lane]) = (uint16_t)((q0 ? 1u : 0u) | (q1 ? 0x100u : 0u));
-    }
-    __syncthreads();
     const bool even_out = (X & 1) == 0;
-    for (int zr = warp; zr < kTile; zr += 8) {
-        const int z = z0 + zr;
-        if (z >= Z) break;
-        const size_t off = (((size_t)v * Z + z) * Y + y) * X + x0;
-        const int xr = 2 * lane, x = x0 + xr;
-        const uint32_t b0 = tile[xr][zr], b1 = tile[xr + 1][zr];
-        if (a.vol_u8) {
-            if (even_out && x + 1 < X) *reinterpret_cast<uint16_t*>(a.vol_u8 + off + xr) = (uint16_t)(b0 | (b1 << 8));
-            else { if (x < X) a.vol_u8[off + xr] = (uint8_t)b0; if (x + 1 < X) a.vol_u8[off + xr + 1] = (uint8_t)b1; }
+    for (int x0 = (xmin / kTile) * kTile; x0 <= xmax; x0 += kTile) {
+        for (int xr = warp; xr < kTile; xr += 8) {
+            const int x = x0 + xr;
+            const int slot = x < X ? slot_v[x] : -1;
+            const uint8_t* src = a.slices + (slot < 0 ? 0 : (size_t)slot * a.slice_pitch) + (size_t)y * Z + z0;
+            const int z = z0 + 2 * lane;
+            uint32_t q0 = 0, q1 = 0;
+            if (slot >= 0) {
+                if (even && z + 1 < Z) { const uint32_t u = __ldg(reinterpret_cast<const uint16_t*>(src) + lane); q0 = u & 0xff; q1 = u >> 8; }
+                else { if (z < Z) q0 = __ldg(src + 2 * lane); if (z + 1 < Z) q1 = __ldg(src + 2 * lane + 1); }
+            }
+            *reinterpret_cast<uint16_t*>(&tile[xr][2 * lane]) = (uint16_t)((q0 ? 1u : 0u) | (q1 ? 0x100u : 0u));
         }
-        if (a.vol_f32) {
-            if (x < X) a.vol_f32[off + xr] = (float)b0;
-            if (x + 1 < X) a.vol_f32[off + xr + 1] = (float)b1;
+        __syncthreads();
+        for (int zr = warp; zr < kTile; zr += 8) {
+            const int z = z0 + zr;
+            if (z >= Z) break;
+            const size_t off = (((size_t)v * Z + z) * Y + y) * X + x0;
+            const int xr = 2 * lane, x = x0 + xr;
+            const uint32_t b0 = tile[xr][zr], b1 = tile[xr + 1][zr];
+            if (a.vol_u8) {
+                if (even_out && x + 1 < X) *reinterpret_cast<uint16_t*>(a.vol_u8 + off + xr) = (uint16_t)(b0 | (b1 << 8));
+                else { if (x < X) a.vol_u8[off + xr] = (uint8_t)b0; if (x + 1 < X) a.vol_u8[off + xr + 1] = (uint8_t)b1; }
+            }
+            if (a.vol_f32) {
+                if (x < X) a.vol_f32[off + xr] = (float)b0;
+                if (x + 1 < X) a.vol_f32[off + xr + 1] = (float)b1;
+            }
         }
+        __syncthreads();
     }
 }
 
@@ -388,7 +389,7 @@ int launch_recon(const uint8_t* slices, size_t slice_pitch, const int32_t* vol_o
     a.X = X; a.Y = Y; a.Z = Z; a.plano = plano; a.nvol = nvol;
     ProfScope prof(K_RECON_GATHER, stream);
     if (plano == MSL_SAGITAL) {
-        dim3 grid(((X + kTile - 1) / kTile) * ((Z + kTile - 1) / kTile), Y, nvol);
+        dim3 grid((Z + kTile - 1) / kTile, Y, nvol);
         recon_sagital_kernel<<<grid, 256, 0, stream>>>(a);
     } else {
         const int W = plano == MSL_AXIAL ? Y : Z;
