@@ -257,7 +257,7 @@ __device__ __forceinline__ void vote_count_word(uint32_t g, uint32_t a, uint32_t
 
 // grid (chunks, nvol).  VEC: 8-byte granules (nvox % 8 == 0 and 8-byte aligned bases) or bytes.
 template <bool VEC>
-__global__ void __launch_bounds__(kCntThreads) consensus_eval_kernel(const VoteArgs a) {
+__global__ void __launch_bounds__(kCntThreads, 4) consensus_eval_kernel(const VoteArgs a) {
     const int v = blockIdx.y;
     const size_t off = (size_t)v * a.nvox;
     Counts4 c[4] = {};
@@ -352,13 +352,13 @@ __global__ void __launch_bounds__(kCntThreads) confusion_counts_kernel(const uin
 inline bool aligned8(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
 
 inline int chunks_for(size_t nvox, int nvol) {
-    // ~16 granules of 8 bytes per thread; at least a couple of waves over 148 SMs for small batches
-    size_t per_cta = (size_t)kCntThreads * 8 * 16;
-    size_t c = (nvox + per_cta - 1) / per_cta;
-    if (c < 1) c = 1;
-    if (c > 4096) c = 4096;
-    (void)nvol;
-    return (int)c;
+    // ~8 resident-CTA waves over 148 SMs in total: long grid-stride loops (loads stay in flight) instead of many
+    // short-lived CTAs; never less than ~2 granules per thread.
+    size_t want = (size_t)(8 * 148 + nvol - 1) / (size_t)nvol;
+    size_t maxc = (nvox / 8 + (size_t)kCntThreads * 2 - 1) / ((size_t)kCntThreads * 2);
+    if (want > maxc) want = maxc;
+    if (want < 1) want = 1;
+    return (int)want;
 }
 
 }  // namespace
