@@ -48,7 +48,7 @@ MEJORAS = ("HE", "CLAHE", "GC", "LT")
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="synthetic patients per GPU per step")
@@ -89,7 +89,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-i", str(self.gpu), "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except OSError:
@@ -323,8 +323,18 @@ def run_ours(args):
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     dk = kernels[dom]
     achieved = dk.get("gb_s", 0.0)
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/r1_traffic.json):
+    # measured dram__bytes_read.sum + dram__bytes_write.sum per pixel of that capture, scaled to this launch size.
+    traffic, traffic_src = None, None
+    tfile = ROOT / "profiles" / "r1_traffic.json"
+    if tfile.exists():
+        tj = json.loads(tfile.read_text()).get(dom)
+        if tj:
+            units_per_launch = alg_bytes.get(dom, 0) / max(1, dk["launches_per_step"]) / tj["algorithmic_bytes_per_unit"]
+            traffic = tj["dram_bytes_per_unit"] * units_per_launch
+            traffic_src = tj["source"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "avg_launch_ms": dk["ms_per_step"] / max(1, dk["launches_per_step"]),
                 "algorithmic_bytes_per_launch": alg_bytes.get(dom, 0) / max(1, dk["launches_per_step"]),
                 "share_of_step": dk["ms_per_step"] / sum(k["ms_per_step"] for k in kernels.values()),
