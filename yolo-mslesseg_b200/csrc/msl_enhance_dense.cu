@@ -58,11 +58,11 @@ constexpr int kOffMisc = 3088;     // int[32]
 constexpr int kOffTabs = 3216;     // xw[cols] f32 | xo[cols] u32 | yw[rows] f32 | yo[rows] u32 | R | su[npx16]
 constexpr int kPairTy = 256 * 20;          // bytes of pair tables per tile row: 256 grays x (9 pairs x 2 B, padded to 20)
 constexpr int kPairBytes = 8 * kPairTy;    // 40,960
-constexpr int kRBytes = kPairBytes + 64 * 256;   // R: tile histograms (first 32 KB) / pair tables (40 KB) + compacted tile LUTs (16 KB)
+constexpr int kHistBytes = 64 * 256 * 4;        // 64 tile histograms, one 32-bit word per bin (packed 16-bit bins make two grays
+                                                // share a word and double the cost of the shared-memory atomics: profiles/microbench)
+constexpr int kRBytes = kHistBytes;             // R: tile histograms (64 KB), later pair tables (40 KB) + tile LUTs (16 KB)
 
-__device__ __forceinline__ unsigned add_hist16(unsigned* ht, int bin) {
-    return atomicAdd(&ht[bin >> 1], 1u << ((bin & 1) * 16));
-}
+__device__ __forceinline__ void add_hist(unsigned* ht, int bin) { atomicAdd(&ht[bin], 1u); }
 
 template <bool DO_CLAHE>
 __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseParams p) {
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
     if (tid == 0) misc[0] = 256;
     if (DO_CLAHE) {
         uint4* r4 = reinterpret_cast<uint4*>(R);
-        for (int q = tid; q < 32768 / 16; q += kThreads) r4[q] = make_uint4(0, 0, 0, 0);
+        for (int q = tid; q < kHistBytes / 16; q += kThreads) r4[q] = make_uint4(0, 0, 0, 0);
     }
     // ---------------------------------------------------------------- load
     uint32_t anynz = 0;
@@ -159,8 +159,9 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
     }
 
     const int th = p.th, tw = p.tw;
-    unsigned* hist = reinterpret_cast<unsigned*>(R);        // 64 tiles x 128 words (two 16-bit bins per word)
-    uint8_t* tya = R + 32768;                                // [rows] tile row of every P column
+    unsigned* hist = reinterpret_cast<unsigned*>(R);        // 64 tiles x 256 bins
+    uint8_t* tya = smem + kOffTabs;                          // [rows] tile row of every P column (the weight tables that
+                                                             // live here are only written after the histogram pass)
     uint8_t* txr = tya + ((rows + 3) & ~3);                  // [cols] tile column of every P row
     const uint32_t* su32 = reinterpret_cast<const uint32_t*>(su);
     const int nw = npx >> 2;
@@ -193,35 +194,34 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
                 const int leader = __ffs(zmask) - 1;
                 const int tl = __shfl_sync(FULL, t0, leader);
                 const unsigned same = __ballot_sync(FULL, zw && t0 == tl);
-                if (lane == leader) atomicAdd(&hist[tl * 128], 4u * __popc(same));
-                else if (zw && t0 != tl) atomicAdd(&hist[t0 * 128], 4u);
+                if (lane == leader) atomicAdd(&hist[tl * 256], 4u * __popc(same));
+                else if (zw && t0 != tl) atomicAdd(&hist[t0 * 256], 4u);
             }
             if (!live || zw) continue;
             if (inrow) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int t = (k == 0) ? t0 : (k == 3 ? t3i : tya[c + k] * 8 + tx);
-                    add_hist16(hist + t * 128, (w >> (8 * k)) & 0xff);
+                    add_hist(hist + t * 256, (w >> (8 * k)) & 0xff);
                 }
             } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    add_hist16(hist + (tya[c] * 8 + txr[r]) * 128, (w >> (8 * k)) & 0xff);
+                    add_hist(hist + (tya[c] * 8 + txr[r]) * 256, (w >> (8 * k)) & 0xff);
                     if (++c == W) { c = 0; ++r; }
                 }
             }
         }
         for (int o = (nw << 2) + tid; o < npx; o += kThreads) {
             const int r = o / W, c = o - r * W;
-            add_hist16(hist + (tya[c] * 8 + txr[r]) * 128, su[o]);
+            add_hist(hist + (tya[c] * 8 + txr[r]) * 256, su[o]);
         }
         __syncthreads();
         // HE's histogram = sum of the 64 tile histograms (before the CLAHE padding is added)
         if (want_he && tid < 256) {
-            const uint16_t* h16 = reinterpret_cast<const uint16_t*>(hist);
             unsigned acc = 0;
 #pragma unroll 8
-            for (int t = 0; t < 64; ++t) acc += h16[t * 256 + tid];
+            for (int t = 0; t < 64; ++t) acc += hist[t * 256 + tid];
             he_hist[tid] = acc;
         }
         __syncthreads();
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
             if (i < nA) { ap = rows + i / pcol; bp = i % pcol; }
             else { const int j = i - nA, wp = pcol - cols; ap = j / wp; bp = cols + j % wp; }
             const int a = reflect101(ap, rows), b = reflect101(bp, cols);
-            add_hist16(hist + ((ap / th) * 8 + bp / tw) * 128, su[(cols - 1 - b) * W + a]);
+            add_hist(hist + ((ap / th) * 8 + bp / tw) * 256, su[(cols - 1 - b) * W + a]);
         }
     } else if (want_he) {
         // HE without CLAHE: plain 256-bin histogram, zero words skipped
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
     // ---------------------------------------------------------------- CLAHE: fold u-bins into L-bins, clip, CDF -> tile LUTs
     // (OpenCV CLAHE_CalcLut_Body).  One warp per tile, 8 L-bins per lane.
     for (int t = warp; t < 64; t += kWarps) {
-        const uint16_t* hu = reinterpret_cast<const uint16_t*>(hist + t * 128);
+        const unsigned* hu = hist + t * 256;
         int hb[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
             uint32_t o = sat_u8_rn(__fmul_rn((float)(hb[k] + excl), p.lut_scale));
             if (k < 4) lo |= o << (8 * k); else hi |= o << (8 * (k - 4));
         }
-        reinterpret_cast<uint2*>(R + kPairBytes + t * 256)[lane] = make_uint2(lo, hi);      // T[t][L], compact, behind the pair area
+        reinterpret_cast<uint2*>(hist + t * 256)[lane] = make_uint2(lo, hi);      // T[t][L]: 256 bytes at the head of the tile's own slot
     }
     // interpolation tables (OpenCV CLAHE_Interpolation_Body): blend weight + table offsets per P row / P column.
     //   P row r    (slice column b): weight xa, pair slot j = floor(txf) + 1 in [0, 8]  -> byte offset 2*j
@@ -376,7 +376,21 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
     // Thread = one gray level u and four tile rows: 8 byte reads (neighbouring u -> neighbouring L: conflict-free)
     // and five 32-bit stores per tile row.
     {
-        const uint8_t* Tc = R + kPairBytes;                  // [64][256]
+        // (the tile LUTs move out of the way first: slots of 1 KB -> a compact [64][256] block behind the pair area)
+        uint8_t* Tc = R + kPairBytes;
+        uint2 tv[(64 * 32 + kThreads - 1) / kThreads];
+#pragma unroll
+        for (int j = 0; j < (64 * 32 + kThreads - 1) / kThreads; ++j) {
+            const int e = tid + j * kThreads;              // tile e / 32, 8-byte piece e % 32
+            if (e < 64 * 32) tv[j] = reinterpret_cast<const uint2*>(R + (e >> 5) * 1024)[e & 31];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < (64 * 32 + kThreads - 1) / kThreads; ++j) {
+            const int e = tid + j * kThreads;
+            if (e < 64 * 32) reinterpret_cast<uint2*>(Tc + (e >> 5) * 256)[e & 31] = tv[j];
+        }
+        __syncthreads();
         const int uv = tid & 255, L = lutl[uv];
         for (int ty = tid >> 8; ty < 8; ty += kThreads / 256) {
             uint32_t t[8];
@@ -408,22 +422,32 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
             const uint8_t* P1 = R + (yoff & 0xffff);
             const uint8_t* P2 = R + (yoff >> 16);
             const int r_end = min(cols, (band + 1) * band_rows);
-            for (int r = band * band_rows; r < r_end; ++r) {
+            auto blend = [&](int r, uint32_t v) -> uint8_t {
                 const float xa = xw[r], xa1 = __fsub_rn(1.0f, xa);
-                const uint32_t off = 20u * su[r * W + c] + xo[r];
+                const uint32_t off = 20u * v + xo[r];
                 const uint32_t h1 = *reinterpret_cast<const uint16_t*>(P1 + off);
                 const uint32_t h2 = *reinterpret_cast<const uint16_t*>(P2 + off);
-                // uint8 -> float without the conversion pipe: bits(2^23 + b) - 2^23
-                const float l11 = __fsub_rn(__uint_as_float(0x4b000000u | (h1 & 0xff)), 8388608.0f);
-                const float l12 = __fsub_rn(__uint_as_float(0x4b000000u | (h1 >> 8)), 8388608.0f);
-                const float l21 = __fsub_rn(__uint_as_float(0x4b000000u | (h2 & 0xff)), 8388608.0f);
-                const float l22 = __fsub_rn(__uint_as_float(0x4b000000u | (h2 >> 8)), 8388608.0f);
+                // uint8 -> float without the conversion pipe: bits(2^23 + b) - 2^23 (PRMT builds the bits)
+                const float l11 = __fsub_rn(__uint_as_float(__byte_perm(h1, 0x4b000000u, 0x7540)), 8388608.0f);
+                const float l12 = __fsub_rn(__uint_as_float(__byte_perm(h1, 0x4b000000u, 0x7541)), 8388608.0f);
+                const float l21 = __fsub_rn(__uint_as_float(__byte_perm(h2, 0x4b000000u, 0x7540)), 8388608.0f);
+                const float l22 = __fsub_rn(__uint_as_float(__byte_perm(h2, 0x4b000000u, 0x7541)), 8388608.0f);
                 const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
                 const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
                 const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
                 // cvRound (half-even) of a value in [0, 255.0001]: the low mantissa bits of res + 1.5 * 2^23
-                su[r * W + c] = lutout[__float_as_uint(__fadd_rn(res, 12582912.0f)) & 0xffu];
+                return lutout[__float_as_uint(__fadd_rn(res, 12582912.0f)) & 0xffu];
+            };
+            // two rows per iteration: both pixels are read before either result is written back, so the two
+            // dependent chains (pixel -> pair table -> blend -> LUT_OUT) overlap
+            int r = band * band_rows;
+            for (; r + 1 < r_end; r += 2) {
+                const uint32_t v0 = su[r * W + c], v1 = su[(r + 1) * W + c];
+                const uint8_t g0 = blend(r, v0), g1 = blend(r + 1, v1);
+                su[r * W + c] = g0;
+                su[(r + 1) * W + c] = g1;
             }
+            if (r < r_end) su[r * W + c] = blend(r, su[r * W + c]);
         }
     }
     __syncthreads();
