@@ -89,6 +89,17 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
     const uint8_t* in = p.U + s * p.u_pitch;
     const bool want_he = p.out_he != nullptr, want_lut = want_he || p.out_gc || p.out_lt;
 
+    // ---------------------------------------------------------------- load
+    // The slice's 128-bit loads are issued first; the table copies and the histogram clear overlap their latency.
+    constexpr int kMaxVec = 4;                                   // 4 x 16 B per thread in flight (covers 48 KB slices)
+    const int nvec = npx >> 4;
+    const uint4* in4 = reinterpret_cast<const uint4*>(in);
+    uint4 pre[kMaxVec];
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+        const int q = tid + j * kThreads;
+        pre[j] = q < nvec ? __ldg(in4 + q) : make_uint4(0, 0, 0, 0);
+    }
     if (tid < 128) reinterpret_cast<uint32_t*>(lutl)[tid] = __ldg(reinterpret_cast<const uint32_t*>(p.tables) + tid);  // LUT_L + LUT_OUT
     if (tid < 256) he_hist[tid] = 0;
     if (tid == 0) misc[0] = 256;
@@ -96,13 +107,15 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
         uint4* r4 = reinterpret_cast<uint4*>(R);
         for (int q = tid; q < kHistBytes / 16; q += kThreads) r4[q] = make_uint4(0, 0, 0, 0);
     }
-    // ---------------------------------------------------------------- load
     uint32_t anynz = 0;
     {
-        const int nvec = npx >> 4;
-        const uint4* in4 = reinterpret_cast<const uint4*>(in);
         uint4* su4 = reinterpret_cast<uint4*>(su);
-        for (int q = tid; q < nvec; q += kThreads) { const uint4 v = __ldg(in4 + q); su4[q] = v; anynz |= v.x | v.y | v.z | v.w; }
+#pragma unroll
+        for (int j = 0; j < kMaxVec; ++j) {
+            const int q = tid + j * kThreads;
+            if (q < nvec) { su4[q] = pre[j]; anynz |= pre[j].x | pre[j].y | pre[j].z | pre[j].w; }
+        }
+        for (int q = tid + kMaxVec * kThreads; q < nvec; q += kThreads) { const uint4 v = __ldg(in4 + q); su4[q] = v; anynz |= v.x | v.y | v.z | v.w; }
         for (int o = (nvec << 4) + tid; o < npx; o += kThreads) { const uint32_t b = __ldg(in + o); su[o] = (uint8_t)b; anynz |= b; }
     }
     // Blank slice (the skull-stripped volumes have ~15 % of them per plane): every output is a constant.
@@ -218,23 +231,29 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
         }
         __syncthreads();
         // HE's histogram = sum of the 64 tile histograms (before the CLAHE padding is added)
-        if (want_he && tid < 256) {
+        if (want_he) {
+            // thread = one gray level and a third of the tiles (768 threads = 3 x 256); partial sums meet in he_hist
+            constexpr int kParts = kThreads / 256;
+            const int part = tid >> 8, u = tid & 255;
             unsigned acc = 0;
-#pragma unroll 8
-            for (int t = 0; t < 64; ++t) acc += hist[t * 256 + tid];
-            he_hist[tid] = acc;
+            for (int t = part; t < 64; t += kParts) acc += hist[t * 256 + u];
+            if (acc) atomicAdd(&he_hist[u], acc);
         }
         __syncthreads();
         // BORDER_REFLECT_101 padding (OpenCV pads bottom / right up to the 8x8 tile grid): the few padded pixels
         const int prow = th * 8, pcol = tw * 8;
         const int nA = (prow - rows) * pcol;                 // padded slice rows, all padded columns
         const int nB = rows * (pcol - cols);                 // real slice rows, padded columns
-        for (int i = tid; i < nA + nB; i += kThreads) {
-            int ap, bp;
-            if (i < nA) { ap = rows + i / pcol; bp = i % pcol; }
-            else { const int j = i - nA, wp = pcol - cols; ap = j / wp; bp = cols + j % wp; }
-            const int a = reflect101(ap, rows), b = reflect101(bp, cols);
-            add_hist(hist + ((ap / th) * 8 + bp / tw) * 256, su[(cols - 1 - b) * W + a]);
+        // region A: padded slice rows ap in [rows, prow), every padded column; region B: real rows, padded columns
+        for (int bp = tid; bp < pcol; bp += kThreads) {
+            const int b = reflect101(bp, cols), tcol = bp / tw, prow_off = (cols - 1 - b) * W;
+            for (int ap = rows; ap < prow; ++ap)
+                add_hist(hist + ((ap / th) * 8 + tcol) * 256, su[prow_off + reflect101(ap, rows)]);
+        }
+        for (int a = tid; a < rows; a += kThreads) {
+            const int trow = tya[a] * 8;
+            for (int bp = cols; bp < pcol; ++bp)
+                add_hist(hist + (trow + bp / tw) * 256, su[(cols - 1 - reflect101(bp, cols)) * W + a]);
         }
     } else if (want_he) {
         // HE without CLAHE: plain 256-bin histogram, zero words skipped
