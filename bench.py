@@ -307,7 +307,7 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     npx = {"axial": 182 * 218, "coronal": 182 * 182, "sagital": 218 * 182}
-    chunk = int(os.environ.get("MSL_VOLUME_CHUNK", "16"))
+    chunk = int(os.environ.get("MSL_VOLUME_CHUNK", "32"))
     nchunks = -(-B // chunk)
     alg_bytes = {   # algorithmic bytes over ONE step, per kernel kind
         "enhance_dense": (1 + 4) * 3 * B * N_VOX,      # per plane: staged uint8 slice in, HE + CLAHE + GC + LT out

@@ -81,7 +81,7 @@ static size_t u_stack_bytes_per_volume(int X, int Y, int Z) {
 
 static int enhance_chunk_volumes(void) {
     const char* e = getenv("MSL_VOLUME_CHUNK");
-    int c = e ? atoi(e) : 16;
+    int c = e ? atoi(e) : 32;
     return c < 1 ? 1 : c;
 }
 
