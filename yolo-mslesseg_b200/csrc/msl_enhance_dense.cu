@@ -190,44 +190,40 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
         for (int a = tid; a < rows; a += kThreads) tya[a] = (uint8_t)(a / th);
         for (int r = tid; r < cols; r += kThreads) txr[r] = (uint8_t)((cols - 1 - r) / tw);
         __syncthreads();
-        for (int q0 = warp * 32; q0 < nw; q0 += kThreads) {      // warp-uniform trip count: ballots inside
-            const int q = q0 + lane;
-            const bool live = q < nw;
-            const unsigned o = 4u * (live ? q : 0);
-            int r = (int)__umulhi(o, p.magic_w);
-            int c = (int)o - r * W;
-            const uint32_t w = live ? su32[q] : 1u;
-            const bool inrow = c + 3 < W;
-            int t0 = 0, t3i = 0, tx = 0;
-            if (inrow) { tx = txr[r]; t0 = tya[c] * 8 + tx; t3i = tya[c + 3] * 8 + tx; }
-            // zero words inside one tile: neighbouring lanes all hit the same bin -> one atomic per warp and tile
-            const bool zw = live && inrow && w == 0 && t0 == t3i;
-            const unsigned zmask = __ballot_sync(FULL, zw);
-            if (zmask) {
-                const int leader = __ffs(zmask) - 1;
-                const int tl = __shfl_sync(FULL, t0, leader);
-                const unsigned same = __ballot_sync(FULL, zw && t0 == tl);
-                if (lane == leader) atomicAdd(&hist[tl * 256], 4u * __popc(same));
-                else if (zw && t0 != tl) atomicAdd(&hist[t0 * 256], 4u);
-            }
-            if (!live || zw) continue;
-            if (inrow) {
+        // Column-major walk (same decomposition as the blend): a lane owns one P column (slice row -> its tile row is a
+        // register), the tile column changes only every tw rows and is warp-uniform.  Background pixels are counted in a
+        // register and flushed once per tile, the others cost one atomic on a 32-bit bin.
+        {
+            const int nchunk = (W + 31) >> 5;
+            const int nband = 8, band_rows = (cols + nband - 1) / nband;
+            for (int task = warp; task < nchunk * nband; task += kWarps) {
+                const int cc = task % nchunk, band = task / nchunk;
+                const int c = cc * 32 + lane;
+                if (c >= W) continue;
+                unsigned* hrow = hist + tya[c] * 8 * 256;                    // first tile of this lane's tile row
+                const int r0 = band * band_rows, r_end = min(cols, r0 + band_rows);
+                if (r0 >= r_end) continue;
+                int zc = 0, tx_cur = txr[r0];
+                const uint8_t* px = su + r0 * W + c;
+                int r = r0;
+                for (; r + 3 < r_end; r += 4, px += 4 * W) {
+                    const uint32_t v0 = px[0], v1 = px[W], v2 = px[2 * W], v3 = px[3 * W];    // loads first, atomics after
+                    const uint32_t vv[4] = {v0, v1, v2, v3};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int t = (k == 0) ? t0 : (k == 3 ? t3i : tya[c + k] * 8 + tx);
-                    add_hist(hist + t * 256, (w >> (8 * k)) & 0xff);
+                    for (int k = 0; k < 4; ++k) {
+                        const int tx = txr[r + k];
+                        if (tx != tx_cur) { if (zc) atomicAdd(&hrow[tx_cur * 256], (unsigned)zc); zc = 0; tx_cur = tx; }
+                        if (vv[k]) atomicAdd(&hrow[tx * 256 + vv[k]], 1u); else ++zc;
+                    }
                 }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    add_hist(hist + (tya[c] * 8 + txr[r]) * 256, (w >> (8 * k)) & 0xff);
-                    if (++c == W) { c = 0; ++r; }
+                for (; r < r_end; ++r, px += W) {
+                    const int tx = txr[r];
+                    if (tx != tx_cur) { if (zc) atomicAdd(&hrow[tx_cur * 256], (unsigned)zc); zc = 0; tx_cur = tx; }
+                    const uint32_t v = px[0];
+                    if (v) atomicAdd(&hrow[tx * 256 + v], 1u); else ++zc;
                 }
+                if (zc) atomicAdd(&hrow[tx_cur * 256], (unsigned)zc);
             }
-        }
-        for (int o = (nw << 2) + tid; o < npx; o += kThreads) {
-            const int r = o / W, c = o - r * W;
-            add_hist(hist + (tya[c] * 8 + txr[r]) * 256, su[o]);
         }
         __syncthreads();
         // HE's histogram = sum of the 64 tile histograms (before the CLAHE padding is added)
