@@ -203,26 +203,26 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
                 unsigned* hrow = hist + tya[c] * 8 * 256;                    // first tile of this lane's tile row
                 const int r0 = band * band_rows, r_end = min(cols, r0 + band_rows);
                 if (r0 >= r_end) continue;
-                int zc = 0, tx_cur = txr[r0];
-                const uint8_t* px = su + r0 * W + c;
-                int r = r0;
-                for (; r + 3 < r_end; r += 4, px += 4 * W) {
-                    const uint32_t v0 = px[0], v1 = px[W], v2 = px[2 * W], v3 = px[3 * W];    // loads first, atomics after
-                    const uint32_t vv[4] = {v0, v1, v2, v3};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int tx = txr[r + k];
-                        if (tx != tx_cur) { if (zc) atomicAdd(&hrow[tx_cur * 256], (unsigned)zc); zc = 0; tx_cur = tx; }
-                        if (vv[k]) atomicAdd(&hrow[tx * 256 + vv[k]], 1u); else ++zc;
-                    }
-                }
-                for (; r < r_end; ++r, px += W) {
+                // rows of one tile column form a segment: P row r belongs to tile column (cols-1-r) / tw
+                for (int r = r0; r < r_end;) {
                     const int tx = txr[r];
-                    if (tx != tx_cur) { if (zc) atomicAdd(&hrow[tx_cur * 256], (unsigned)zc); zc = 0; tx_cur = tx; }
-                    const uint32_t v = px[0];
-                    if (v) atomicAdd(&hrow[tx * 256 + v], 1u); else ++zc;
+                    const int seg_end = min(r_end, cols - tx * tw);
+                    unsigned* ht = hrow + tx * 256;
+                    const uint8_t* px = su + r * W + c;
+                    int zc = 0;
+                    for (; r + 3 < seg_end; r += 4, px += 4 * W) {
+                        const uint32_t v0 = px[0], v1 = px[W], v2 = px[2 * W], v3 = px[3 * W];    // loads first, atomics after
+                        if (v0) atomicAdd(&ht[v0], 1u); else ++zc;
+                        if (v1) atomicAdd(&ht[v1], 1u); else ++zc;
+                        if (v2) atomicAdd(&ht[v2], 1u); else ++zc;
+                        if (v3) atomicAdd(&ht[v3], 1u); else ++zc;
+                    }
+                    for (; r < seg_end; ++r, px += W) {
+                        const uint32_t v = px[0];
+                        if (v) atomicAdd(&ht[v], 1u); else ++zc;
+                    }
+                    if (zc) atomicAdd(&ht[0], (unsigned)zc);
                 }
-                if (zc) atomicAdd(&hrow[tx_cur * 256], (unsigned)zc);
             }
         }
         __syncthreads();
