@@ -9,14 +9,18 @@
 //         LUT_OUT[clahe(LUT_L[u])], OpenCV imgproc/clahe.cpp), GC (E5, :139-151) and LT (E6, :166-184) slices,
 //         densely packed, same orientation.  One CTA per slice; all enhancements share one shared-memory copy.
 //
-// The kernel moves 2-5 B per pixel but is bound by shared-memory wavefronts and instruction issue, so:
-//  * ONE set of histograms: 64 tile histograms over u (two 16-bit bins per word).  HE's global histogram is their
-//    sum; CLAHE's histograms over L = LUT_L[u] are segment sums of the u-bins (LUT_L is monotone).  Zero words
-//    (skull-stripped background, ~3/4 of the pixels) cost one atomic per four pixels.
-//  * HE / GC / LT are applied through one packed 32-bit table (one lookup per pixel for all three).
-//  * CLAHE tile LUTs are composed with LUT_L and widened to float once per slice, the blend weights / tile
-//    offsets per row and column are tabulated, consecutive lanes take consecutive pixels, and round-half-even
-//    goes through the 1.5*2^23 magic add instead of F2I.
+// The kernel moves 2-5 B per pixel but is bound by shared-memory latency and instruction issue, so:
+//  * ONE set of histograms: 64 tile histograms over u, one 32-bit word per bin (packed 16-bit bins double the cost of
+//    the shared-memory atomics, profiles/microbench).  HE's global histogram is their sum; CLAHE's histograms over
+//    L = LUT_L[u] are segment sums of the u-bins (LUT_L is monotone).  A thread walks one P column (constant tile
+//    row) in segments of constant tile column, so the histogram base is hoisted out of the pixel loop.
+//  * HE / GC / LT are applied through one packed 32-bit table (one lookup per pixel for all three) and transposed
+//    into three output words with PRMT.
+//  * CLAHE tile LUTs are composed with LUT_L once per slice into "pair tables": for each tile row and gray the 9
+//    horizontally adjacent (left, right) LUT byte pairs, 20 B per gray, so a pixel's four corners are two 16-bit
+//    loads.  Blend weights and pair offsets per P row / column are tabulated, bytes are widened to float with
+//    PRMT + magic subtract, and round-half-even goes through the 1.5*2^23 magic add instead of F2I.
+//  * A slice that normalised to all zeros (outside the brain) skips every phase: outputs are table[0] constants.
 #include "msl_common.cuh"
 #include "msl_kernels.h"
 
@@ -62,7 +66,7 @@ constexpr int kHistBytes = 64 * 256 * 4;        // 64 tile histograms, one 32-bi
                                                 // share a word and double the cost of the shared-memory atomics: profiles/microbench)
 constexpr int kRBytes = kHistBytes;             // R: tile histograms (64 KB), later pair tables (40 KB) + tile LUTs (16 KB)
 
-__device__ __forceinline__ void add_hist(unsigned* ht, int bin) { atomicAdd(&ht[bin], 1u); }
+__device__ __forceinline__ void add_hist(unsigned* ht, int bin) { if (bin) atomicAdd(&ht[bin], 1u); }   // bin 0 is implicit
 
 template <bool DO_CLAHE>
 __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseParams p) {
@@ -175,7 +179,6 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
     unsigned* hist = reinterpret_cast<unsigned*>(R);        // 64 tiles x 256 bins
     uint8_t* tya = smem + kOffTabs;                          // [rows] tile row of every P column (the weight tables that
                                                              // live here are only written after the histogram pass)
-    uint8_t* txr = tya + ((rows + 3) & ~3);                  // [cols] tile column of every P row
     const uint32_t* su32 = reinterpret_cast<const uint32_t*>(su);
     const int nw = npx >> 2;
 
@@ -188,40 +191,32 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
             ustart[tid] = (uint16_t)lo;
         }
         for (int a = tid; a < rows; a += kThreads) tya[a] = (uint8_t)(a / th);
-        for (int r = tid; r < cols; r += kThreads) txr[r] = (uint8_t)((cols - 1 - r) / tw);
         __syncthreads();
         // Column-major walk (same decomposition as the blend): a lane owns one P column (slice row -> its tile row is a
-        // register), the tile column changes only every tw rows and is warp-uniform.  Background pixels are counted in a
-        // register and flushed once per tile, the others cost one atomic on a 32-bit bin.
+        // register), the tile column changes only every tw rows and is warp-uniform.  Background pixels (u == 0) are
+        // never counted: every padded tile holds th * tw pixels, so bin 0 is recovered by subtraction in the fold below
+        // (and HE's bin 0 in its CDF); four rows that are background in all 32 columns cost four loads and a branch.
         {
             const int nchunk = (W + 31) >> 5;
-            const int nband = 8, band_rows = (cols + nband - 1) / nband;
-            for (int task = warp; task < nchunk * nband; task += kWarps) {
-                const int cc = task % nchunk, band = task / nchunk;
+            for (int task = warp; task < nchunk * 8; task += kWarps) {
+                const int cc = task % nchunk, tx = 7 - task / nchunk;       // band = the P rows of tile column tx
                 const int c = cc * 32 + lane;
-                if (c >= W) continue;
-                unsigned* hrow = hist + tya[c] * 8 * 256;                    // first tile of this lane's tile row
-                const int r0 = band * band_rows, r_end = min(cols, r0 + band_rows);
-                if (r0 >= r_end) continue;
-                // rows of one tile column form a segment: P row r belongs to tile column (cols-1-r) / tw
-                for (int r = r0; r < r_end;) {
-                    const int tx = txr[r];
-                    const int seg_end = min(r_end, cols - tx * tw);
-                    unsigned* ht = hrow + tx * 256;
-                    const uint8_t* px = su + r * W + c;
-                    int zc = 0;
-                    for (; r + 3 < seg_end; r += 4, px += 4 * W) {
-                        const uint32_t v0 = px[0], v1 = px[W], v2 = px[2 * W], v3 = px[3 * W];    // loads first, atomics after
-                        if (v0) atomicAdd(&ht[v0], 1u); else ++zc;
-                        if (v1) atomicAdd(&ht[v1], 1u); else ++zc;
-                        if (v2) atomicAdd(&ht[v2], 1u); else ++zc;
-                        if (v3) atomicAdd(&ht[v3], 1u); else ++zc;
-                    }
-                    for (; r < seg_end; ++r, px += W) {
-                        const uint32_t v = px[0];
-                        if (v) atomicAdd(&ht[v], 1u); else ++zc;
-                    }
-                    if (zc) atomicAdd(&ht[0], (unsigned)zc);
+                const int r0 = max(0, cols - (tx + 1) * tw), r_end = cols - tx * tw;
+                if (c >= W || r0 >= r_end) continue;
+                unsigned* ht = hist + (tya[c] * 8 + tx) * 256;
+                const uint8_t* px = su + r0 * W + c;
+                int r = r0;
+                for (; r + 3 < r_end; r += 4, px += 4 * W) {
+                    const uint32_t v0 = px[0], v1 = px[W], v2 = px[2 * W], v3 = px[3 * W];    // loads first, atomics after
+                    if ((v0 | v1 | v2 | v3) == 0) continue;
+                    if (v0) atomicAdd(&ht[v0], 1u);
+                    if (v1) atomicAdd(&ht[v1], 1u);
+                    if (v2) atomicAdd(&ht[v2], 1u);
+                    if (v3) atomicAdd(&ht[v3], 1u);
+                }
+                for (; r < r_end; ++r, px += W) {
+                    const uint32_t v = px[0];
+                    if (v) atomicAdd(&ht[v], 1u);
                 }
             }
         }
@@ -238,8 +233,6 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
         __syncthreads();
         // BORDER_REFLECT_101 padding (OpenCV pads bottom / right up to the 8x8 tile grid): the few padded pixels
         const int prow = th * 8, pcol = tw * 8;
-        const int nA = (prow - rows) * pcol;                 // padded slice rows, all padded columns
-        const int nB = rows * (pcol - cols);                 // real slice rows, padded columns
         // region A: padded slice rows ap in [rows, prow), every padded column; region B: real rows, padded columns
         for (int bp = tid; bp < pcol; bp += kThreads) {
             const int b = reflect101(bp, cols), tcol = bp / tw, prow_off = (cols - 1 - b) * W;
@@ -271,6 +264,7 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
 
     // ---------------------------------------------------------------- HE CDF -> LUT; packed HE | GC | LT table
     if (want_lut) {
+        // (with CLAHE on, he_hist[0] is still empty: the background count is npx minus everything else)
         int h = 0, c = 0;
         if (want_he && tid < 256) {
             h = (int)he_hist[tid];
@@ -282,9 +276,13 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
         if (tid < 256) {
             uint32_t he = 0;
             if (want_he) {
-                for (int w = 0; w < warp; ++w) c += misc[1 + w];
-                const int i0 = misc[0];
-                const int h0 = (int)he_hist[i0];
+                int total = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) { const int m = misc[1 + w]; total += m; if (w < warp) c += m; }
+                const int zeros = npx - total;                       // uncounted background pixels (0 without CLAHE)
+                c += zeros;
+                const int i0 = zeros > 0 ? 0 : misc[0];
+                const int h0 = zeros > 0 ? zeros + (int)he_hist[0] : (int)he_hist[i0];
                 if (h0 == npx) he = (uint32_t)i0;
                 else if (tid <= i0) he = 0;
                 else he = sat_u8_rn(__fmul_rn((float)(c - h0), __fdiv_rn(255.0f, (float)(npx - h0))));
@@ -333,7 +331,16 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
             for (int u = u0 + 2; u < u0 + n; ++u) acc += hu[u];
             hb[k] = acc;
         }
-        __syncwarp();
+        {
+            // the tile's background pixels were never counted: th * tw minus everything else, into L-bin LUT_L[0]
+            int tot = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tot += hb[k];
+            const int zeros = th * tw - warp_sum(tot);
+            const int L0 = lutl[0];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (lane * 8 + k == L0) hb[k] += zeros;
+        }
         const int clip = p.clip;
         int clipped = 0;
 #pragma unroll
