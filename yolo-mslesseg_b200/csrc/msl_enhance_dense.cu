@@ -59,7 +59,8 @@ constexpr int kOffUstart = 512;    // u16[257] first u whose LUT_L[u] >= L     (
 constexpr int kOffT3 = 1040;       // u32[256] he | gc << 8 | lt << 16
 constexpr int kOffHeHist = 2064;   // u32[256]
 constexpr int kOffMisc = 3088;     // int[32]
-constexpr int kOffTabs = 3216;     // xw[cols] f32 | xo[cols] u32 | yw[rows] f32 | yo[rows] u32 | R | su[npx16]
+constexpr int kOffFold = 3216;     // u32[256] byte offsets of the (up to) two u-bins that fold into L-bin L: lo16 | hi16
+constexpr int kOffTabs = 4240;     // xw[cols] f32 | xo[cols] u32 | yw[rows] f32 | yo[rows] u32 | R | su[npx16]
 constexpr int kPairTy = 256 * 20;          // bytes of pair tables per tile row: 256 grays x (9 pairs x 2 B, padded to 20)
 constexpr int kPairBytes = 8 * kPairTy;    // 40,960
 constexpr int kHistBytes = 64 * 256 * 4;        // 64 tile histograms, one 32-bit word per bin (packed 16-bit bins make two grays
@@ -67,6 +68,12 @@ constexpr int kHistBytes = 64 * 256 * 4;        // 64 tile histograms, one 32-bi
 constexpr int kRBytes = kHistBytes;             // R: tile histograms (64 KB), later pair tables (40 KB) + tile LUTs (16 KB)
 
 __device__ __forceinline__ void add_hist(unsigned* ht, int bin) { if (bin) atomicAdd(&ht[bin], 1u); }   // bin 0 is implicit
+
+// floor(a / b) for 0 <= a < 2^16, 1 <= b <= 256 without the integer-division sequence: the approximate quotient is biased
+// up by 4e-6 (more than its error, less than the 1 / b gap below the next integer).
+__device__ __forceinline__ int small_div(int a, int b) {
+    return (int)__fmul_rn(__fdividef((float)a, (float)b), 1.000004f);
+}
 
 template <bool DO_CLAHE>
 __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseParams p) {
@@ -76,7 +83,8 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
     uint16_t* ustart = reinterpret_cast<uint16_t*>(smem + kOffUstart);
     uint32_t* t3 = reinterpret_cast<uint32_t*>(smem + kOffT3);
     unsigned* he_hist = reinterpret_cast<unsigned*>(smem + kOffHeHist);
-    int* misc = reinterpret_cast<int*>(smem + kOffMisc);       // [0] i0, [1..16] warp scan totals
+    int* misc = reinterpret_cast<int*>(smem + kOffMisc);       // [0] i0, [1..16] warp scan totals, [20] blank-slice value, [21] long folds
+    uint32_t* fold = reinterpret_cast<uint32_t*>(smem + kOffFold);
     const int rows = p.rows, cols = p.cols, npx = rows * cols;
     const int W = rows;                                          // P row length
     float* xw = reinterpret_cast<float*>(smem + kOffTabs);       // indexed by P row r   (slice column b = cols-1-r)
@@ -106,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
     }
     if (tid < 128) reinterpret_cast<uint32_t*>(lutl)[tid] = __ldg(reinterpret_cast<const uint32_t*>(p.tables) + tid);  // LUT_L + LUT_OUT
     if (tid < 256) he_hist[tid] = 0;
-    if (tid == 0) misc[0] = 256;
+    if (tid == 0) { misc[0] = 256; misc[21] = 0; }
     if (DO_CLAHE) {
         uint4* r4 = reinterpret_cast<uint4*>(R);
         for (int q = tid; q < kHistBytes / 16; q += kThreads) r4[q] = make_uint4(0, 0, 0, 0);
@@ -192,6 +200,13 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
         }
         for (int a = tid; a < rows; a += kThreads) tya[a] = (uint8_t)(a / th);
         __syncthreads();
+        if (tid < 256) {
+            // fold table: L-bin tid sums u-bins [ustart, ustart + n).  n <= 2 for cv2's LUT_L: keep two byte offsets, the
+            // unused ones pointing at u-bin 0, which is never counted and stays zero.  n > 2 (other tables): generic loop.
+            const int u0 = ustart[tid], n = (int)ustart[tid + 1] - u0;
+            fold[tid] = (uint32_t)(n > 0 ? u0 * 4 : 0) | ((uint32_t)(n > 1 ? (u0 + 1) * 4 : 0) << 16);
+            if (n > 2) misc[21] = 1;
+        }
         // Column-major walk (same decomposition as the blend): a lane owns one P column (slice row -> its tile row is a
         // register), the tile column changes only every tw rows and is warp-uniform.  Background pixels (u == 0) are
         // never counted: every padded tile holds th * tw pixels, so bin 0 is recovered by subtraction in the fold below
@@ -318,41 +333,50 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
 
     // ---------------------------------------------------------------- CLAHE: fold u-bins into L-bins, clip, CDF -> tile LUTs
     // (OpenCV CLAHE_CalcLut_Body).  One warp per tile, 8 L-bins per lane.
+    const bool long_fold = misc[21] != 0;
+    const int L0 = lutl[0], area = th * tw, clip = p.clip;
     for (int t = warp; t < 64; t += kWarps) {
         const unsigned* hu = hist + t * 256;
         int hb[8];
+        if (!long_fold) {
+            const uint4 f0 = reinterpret_cast<const uint4*>(fold)[lane * 2], f1 = reinterpret_cast<const uint4*>(fold)[lane * 2 + 1];
+            const uint32_t f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+            const uint8_t* hub = reinterpret_cast<const uint8_t*>(hu);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int L = lane * 8 + k;
-            const int u0 = ustart[L], n = (int)ustart[L + 1] - u0;   // cv2's LUT_L folds at most two grays into one L
-            int acc = 0;
-            if (n > 0) acc = hu[u0];
-            if (n > 1) acc += hu[u0 + 1];
-            for (int u = u0 + 2; u < u0 + n; ++u) acc += hu[u];
-            hb[k] = acc;
+            for (int k = 0; k < 8; ++k)
+                hb[k] = (int)(*reinterpret_cast<const unsigned*>(hub + (f[k] & 0xffffu)) + *reinterpret_cast<const unsigned*>(hub + (f[k] >> 16)));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int L = lane * 8 + k;
+                int acc = 0;
+                for (int u = ustart[L]; u < (int)ustart[L + 1]; ++u) acc += (int)hu[u];
+                hb[k] = acc;
+            }
         }
         {
             // the tile's background pixels were never counted: th * tw minus everything else, into L-bin LUT_L[0]
             int tot = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) tot += hb[k];
-            const int zeros = th * tw - warp_sum(tot);
-            const int L0 = lutl[0];
+            const int zeros = area - warp_sum(tot);
+            if (L0 == 0) { if (lane == 0) hb[0] += zeros; }
+            else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) if (lane * 8 + k == L0) hb[k] += zeros;
+                for (int k = 0; k < 8; ++k) if (lane * 8 + k == L0) hb[k] += zeros;
+            }
         }
-        const int clip = p.clip;
         int clipped = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
             if (hb[k] > clip) { clipped += hb[k] - clip; hb[k] = clip; }
         clipped = warp_sum(clipped);
-        const int rb = clipped / 256;
-        const int res = clipped - rb * 256;
+        const int rb = clipped >> 8;
+        const int res = clipped & 255;
         // residual: bins 0, step, 2*step, ... (res of them) get one more; walk this lane's 8 bins without dividing per bin
-        const int step = res > 0 ? max(256 / res, 1) : 256;
+        const int step = res > 0 ? small_div(256, res) : 256;
         const int base = lane * 8;
-        int kn = (base + step - 1) / step;                   // index of the first multiple of step that is >= base
+        int kn = small_div(base + step - 1, step);          // index of the first multiple of step that is >= base
         int nxt = kn * step;
         int run = 0;
 #pragma unroll
@@ -364,12 +388,16 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
             hb[k] = run;
         }
         const int excl = warp_incl_scan(run, lane) - run;
-        uint32_t lo = 0, hi = 0;
+        // saturate_cast<uchar>(cdf * lutScale): the product lies in [0, 255.0001], so int -> float and round-half-even both
+        // go through magic adds and the low byte of the sum is the result
+        uint32_t o[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            uint32_t o = sat_u8_rn(__fmul_rn((float)(hb[k] + excl), p.lut_scale));
-            if (k < 4) lo |= o << (8 * k); else hi |= o << (8 * (k - 4));
+            const float cdf = __fsub_rn(__uint_as_float(0x4b000000u + (uint32_t)(hb[k] + excl)), 8388608.0f);
+            o[k] = __float_as_uint(__fadd_rn(__fmul_rn(cdf, p.lut_scale), 12582912.0f));
         }
+        const uint32_t lo = __byte_perm(__byte_perm(o[0], o[1], 0x0040), __byte_perm(o[2], o[3], 0x0040), 0x5410);
+        const uint32_t hi = __byte_perm(__byte_perm(o[4], o[5], 0x0040), __byte_perm(o[6], o[7], 0x0040), 0x5410);
         reinterpret_cast<uint2*>(hist + t * 256)[lane] = make_uint2(lo, hi);      // T[t][L]: 256 bytes at the head of the tile's own slot
     }
     // interpolation tables (OpenCV CLAHE_Interpolation_Body): blend weight + table offsets per P row / P column.
