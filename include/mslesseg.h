@@ -69,7 +69,8 @@ extern "C" {
  *   [768  , 1024)  CM       matplotlib gray colormap bytes (extraer_dataset.py:192)
  *   [1024 , 1024+65536) LT_T[m][v]  log table for a slice whose maximum is m (mejora_imagen.py:173-182)
  * They are parameters computed on the host with the reference's own NumPy expressions
- * (mslesseg_b200/tables.py); the library only reads them. */
+ * (mslesseg_b200/tables.py); the library only reads them.  LUT_L must be non-decreasing (gray -> L is; the
+ * volume path derives CLAHE's L histograms from the gray histograms through it); the other tables are free. */
 #define MSL_TAB_LUT_L   0
 #define MSL_TAB_LUT_OUT 256
 #define MSL_TAB_GC      512

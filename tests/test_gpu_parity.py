@@ -128,6 +128,34 @@ def test_noise_volume_golden(ops, torch_mod, golden, cuda_device):
             assert sha(G) == g["planes"][plano][mej], (plano, mej, "volume mode")
 
 
+def test_volume_mode_custom_tables(ops, torch_mod, cuda_device):
+    """The table block is a parameter: any non-decreasing LUT_L must work (the volume path folds gray histograms into
+    L histograms through it).  This one starts above 0, folds up to four grays into one L and leaves gaps."""
+    torch = torch_mod
+    from mslesseg_b200 import tables as T
+    lut_l = np.minimum(3 + (np.arange(256) // 4) * 5 + (np.arange(256) % 4 == 3) * 2, 255).astype(np.uint8)
+    assert np.all(np.diff(lut_l.astype(int)) >= 0) and lut_l[0] != 0
+    lut_out = (255 - np.arange(256)).astype(np.uint8)
+    host = T.host_tables().copy()
+    host[T.TAB_LUT_L:T.TAB_LUT_L + 256] = lut_l
+    host[T.TAB_LUT_OUT:T.TAB_LUT_OUT + 256] = lut_out
+    tables = torch.from_numpy(host).to(cuda_device)
+    nv = _noise(4242, (45, 37, 41))
+    nv[:, :9, :] = 0                      # a background band so that blank tiles and blank slices occur too
+    nv[:3] = 0
+    vol = torch.from_numpy(nv).to(cuda_device)[None].contiguous()
+    vxyz = S.as_xyz(nv).astype(np.float64)
+    res = ops.enhance_volumes(vol, mejoras=("CLAHE", "HE"), tables=tables)
+    for plano in PLANOS:
+        n_p = vxyz.shape[O.plane_axis(plano)]
+        want_cl = np.stack([lut_out[O.clahe_apply(lut_l[O.normalizar_a_uint8(O.slice_of(vxyz, plano, i))])] for i in range(n_p)])
+        G = res[("CLAHE", plano)][0].flip(-2).transpose(-1, -2).contiguous().cpu().numpy()
+        assert np.array_equal(G, want_cl), explain(G, want_cl, f"custom tables {plano} CLAHE")
+        want_he = oracle_all(vxyz, plano, "HE")
+        G = res[("HE", plano)][0].flip(-2).transpose(-1, -2).contiguous().cpu().numpy()
+        assert np.array_equal(G, want_he), explain(G, want_he, f"custom tables {plano} HE")
+
+
 @pytest.mark.parametrize("shape_xyz", [(37, 45, 29), (8, 8, 8), (64, 24, 16), (33, 18, 50)])
 def test_odd_shapes_vs_oracle(ops, torch_mod, cuda_device, shape_xyz):
     torch = torch_mod

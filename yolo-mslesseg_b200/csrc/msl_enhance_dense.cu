@@ -62,10 +62,11 @@ constexpr int kOffMisc = 3088;     // int[32]
 constexpr int kOffFold = 3216;     // u32[256] byte offsets of the (up to) two u-bins that fold into L-bin L: lo16 | hi16
 constexpr int kOffTabs = 4240;     // xw[cols] f32 | xo[cols] u32 | yw[rows] f32 | yo[rows] u32 | R | su[npx16]
 constexpr int kPairTy = 256 * 20;          // bytes of pair tables per tile row: 256 grays x (9 pairs x 2 B, padded to 20)
-constexpr int kPairBytes = 8 * kPairTy;    // 40,960
+constexpr int kPairStride = kPairTy + 1024;   // each tile row's pair tables are followed by its background row TZ[ty][r] (<= 256 floats)
+constexpr int kPairBytes = 8 * kPairStride;   // 49,152
 constexpr int kHistBytes = 64 * 256 * 4;        // 64 tile histograms, one 32-bit word per bin (packed 16-bit bins make two grays
                                                 // share a word and double the cost of the shared-memory atomics: profiles/microbench)
-constexpr int kRBytes = kHistBytes;             // R: tile histograms (64 KB), later pair tables (40 KB) + tile LUTs (16 KB)
+constexpr int kRBytes = kHistBytes;             // R: tile histograms (64 KB), later pair tables + background rows (48 KB) + tile LUTs (16 KB)
 
 __device__ __forceinline__ void add_hist(unsigned* ht, int bin) { if (bin) atomicAdd(&ht[bin], 1u); }   // bin 0 is implicit
 
@@ -402,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
     }
     // interpolation tables (OpenCV CLAHE_Interpolation_Body): blend weight + table offsets per P row / P column.
     //   P row r    (slice column b): weight xa, pair slot j = floor(txf) + 1 in [0, 8]  -> byte offset 2*j
-    //   P column c (slice row a)   : weight ya, tile rows ty1 / ty2                      -> byte offsets ty * kPairTy
+    //   P column c (slice row a)   : weight ya, tile rows ty1 / ty2
     {
         const float inv_tw = __fdiv_rn(1.0f, (float)tw), inv_th = __fdiv_rn(1.0f, (float)th);
         for (int r = tid; r < cols; r += kThreads) {
@@ -416,10 +417,11 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
             const float tyf = __fsub_rn(__fmul_rn((float)a, inv_th), 0.5f);
             const int t1 = (int)floorf(tyf), t2 = t1 + 1;
             yw[a] = __fsub_rn(tyf, (float)t1);
-            yo[a] = (uint32_t)(max(t1, 0) * kPairTy) | ((uint32_t)(min(t2, 7) * kPairTy) << 16);
+            yo[a] = (uint32_t)max(t1, 0) | ((uint32_t)min(t2, 7) << 16);
         }
     }
     __syncthreads();
+    const bool use_tz = cols <= (kPairStride - kPairTy) / 4;
     // Pair tables: PT[ty][u][j] = (T[ty][tx1][LUT_L[u]], T[ty][tx2][LUT_L[u]]) as one 16-bit entry for the nine
     // horizontal neighbour pairs (tx1, tx2) = (0,0), (0,1), ..., (6,7), (7,7).  One 16-bit read fetches both operands
     // of a horizontal blend; a gray level's nine entries take 20 bytes (5 words: odd stride -> spread over the banks).
@@ -446,13 +448,28 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
             uint32_t t[8];
 #pragma unroll
             for (int tx = 0; tx < 8; ++tx) t[tx] = Tc[(ty * 8 + tx) * 256 + L];
-            uint32_t* dst = reinterpret_cast<uint32_t*>(R + ty * kPairTy + uv * 20);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(R + ty * kPairStride + uv * 20);
             // pairs j = 0..8: (t0,t0) (t0,t1) (t1,t2) ... (t6,t7) (t7,t7), two 16-bit pairs per word
             dst[0] = (t[0] | (t[0] << 8)) | ((t[0] | (t[1] << 8)) << 16);
             dst[1] = (t[1] | (t[2] << 8)) | ((t[2] | (t[3] << 8)) << 16);
             dst[2] = (t[3] | (t[4] << 8)) | ((t[4] | (t[5] << 8)) << 16);
             dst[3] = (t[5] | (t[6] << 8)) | ((t[6] | (t[7] << 8)) << 16);
             dst[4] = (t[7] | (t[7] << 8));
+        }
+        // Background rows: for u == 0 the horizontal half of the blend depends only on (tile row, P row).  TZ[ty][r] holds it
+        // (the same two products and sum the per-pixel path computes), so a background pixel needs two loads and the
+        // vertical half.  Lives behind each tile row's pair tables (slices up to 256 P rows; others take the pixel path).
+        if (use_tz) {
+            const int L0 = lutl[0];
+            for (int r = tid; r < cols; r += kThreads) {
+                const int j = (int)(xo[r] >> 1), tx1 = max(j - 1, 0), tx2 = min(j, 7);
+                const float xa = xw[r], xa1 = __fsub_rn(1.0f, xa);
+#pragma unroll
+                for (int ty = 0; ty < 8; ++ty) {
+                    const float lo = (float)Tc[(ty * 8 + tx1) * 256 + L0], hi = (float)Tc[(ty * 8 + tx2) * 256 + L0];
+                    reinterpret_cast<float*>(R + ty * kPairStride + kPairTy)[r] = __fadd_rn(__fmul_rn(lo, xa1), __fmul_rn(hi, xa));
+                }
+            }
         }
     }
     __syncthreads();
@@ -469,8 +486,10 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
             if (c >= W) continue;
             const float ya = yw[c], ya1 = __fsub_rn(1.0f, ya);
             const uint32_t yoff = yo[c];
-            const uint8_t* P1 = R + (yoff & 0xffff);
-            const uint8_t* P2 = R + (yoff >> 16);
+            const uint8_t* P1 = R + (yoff & 0xffff) * kPairStride;
+            const uint8_t* P2 = R + (yoff >> 16) * kPairStride;
+            const float* tz1 = reinterpret_cast<const float*>(P1 + kPairTy);
+            const float* tz2 = reinterpret_cast<const float*>(P2 + kPairTy);
             const int r_end = min(cols, (band + 1) * band_rows);
             auto blend = [&](int r, uint32_t v) -> uint8_t {
                 const float xa = xw[r], xa1 = __fsub_rn(1.0f, xa);
@@ -491,9 +510,15 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
             // two rows per iteration: both pixels are read before either result is written back, so the two
             // dependent chains (pixel -> pair table -> blend -> LUT_OUT) overlap
             int r = band * band_rows;
+            auto blend_bg = [&](int r) -> uint8_t {
+                const float res = __fadd_rn(__fmul_rn(tz1[r], ya1), __fmul_rn(tz2[r], ya));
+                return lutout[__float_as_uint(__fadd_rn(res, 12582912.0f)) & 0xffu];
+            };
             for (; r + 1 < r_end; r += 2) {
                 const uint32_t v0 = su[r * W + c], v1 = su[(r + 1) * W + c];
-                const uint8_t g0 = blend(r, v0), g1 = blend(r + 1, v1);
+                uint8_t g0, g1;
+                if (use_tz && (v0 | v1) == 0) { g0 = blend_bg(r); g1 = blend_bg(r + 1); }
+                else { g0 = blend(r, v0); g1 = blend(r + 1, v1); }
                 su[r * W + c] = g0;
                 su[(r + 1) * W + c] = g1;
             }

@@ -162,10 +162,12 @@ def enhance_volumes_workspace_bytes(nvol: int, X: int, Y: int, Z: int) -> int:
 
 def enhance_volumes(vol: torch.Tensor, mejoras: Iterable[str] = MEJORAS, planos: Iterable[str] = PLANOS,
                     outs: Optional[Dict[Tuple[str, str], torch.Tensor]] = None,
-                    workspace: Optional[torch.Tensor] = None) -> Dict[Tuple[str, str], torch.Tensor]:
+                    workspace: Optional[torch.Tensor] = None,
+                    tables: Optional[torch.Tensor] = None) -> Dict[Tuple[str, str], torch.Tensor]:
     """All slices of the requested planes and enhancements from ONE resident float32 copy.
     Returns {(mejora, plano): uint8 [nvol, n_plane, cols, rows]} in PNG orientation; the slice-oriented
-    view is `P.flip(-2).transpose(-1, -2)`."""
+    view is `P.flip(-2).transpose(-1, -2)`.  `tables`: a device copy of a custom MSL_TABLES_BYTES block
+    (default: the reference's constants, `device_tables`)."""
     _need_cuda(vol, "vol")
     if vol.dim() != 4 or vol.dtype != torch.float32:
         raise ValueError("vol must be float32 [nvol, Z, Y, X]")
@@ -192,7 +194,12 @@ def enhance_volumes(vol: torch.Tensor, mejoras: Iterable[str] = MEJORAS, planos:
     if workspace is None:
         workspace = torch.empty(need, dtype=torch.uint8, device=vol.device)
     _need_cuda(workspace, "workspace")
-    L.check(L.load().msl_enhance_volumes(_ptr(vol), nvol, X, Y, Z, ptrs, _ptr(device_tables(vol.device)),
+    if tables is None:
+        tables = device_tables(vol.device)
+    _need_cuda(tables, "tables")
+    if tables.dtype != torch.uint8 or tables.numel() != T.TABLES_BYTES:
+        raise ValueError(f"tables must be uint8 [{T.TABLES_BYTES}]")
+    L.check(L.load().msl_enhance_volumes(_ptr(vol), nvol, X, Y, Z, ptrs, _ptr(tables),
                                          _ptr(workspace), workspace.numel() * workspace.element_size(), _stream()))
     return result
 
