@@ -483,6 +483,7 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
         for (int task = warp; task < nchunk * nband; task += kWarps) {
             const int cc = task % nchunk, band = task / nchunk;
             const int c = cc * 32 + lane;
+            const unsigned amask = __ballot_sync(0xffffffffu, c < W);
             if (c >= W) continue;
             const float ya = yw[c], ya1 = __fsub_rn(1.0f, ya);
             const uint32_t yoff = yo[c];
@@ -517,7 +518,7 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
             for (; r + 1 < r_end; r += 2) {
                 const uint32_t v0 = su[r * W + c], v1 = su[(r + 1) * W + c];
                 uint8_t g0, g1;
-                if (use_tz && (v0 | v1) == 0) { g0 = blend_bg(r); g1 = blend_bg(r + 1); }
+                if (use_tz && !__any_sync(amask, (v0 | v1) != 0)) { g0 = blend_bg(r); g1 = blend_bg(r + 1); }   // warp-uniform
                 else { g0 = blend(r, v0); g1 = blend(r + 1, v1); }
                 su[r * W + c] = g0;
                 su[(r + 1) * W + c] = g1;
