@@ -474,10 +474,11 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
     }
     __syncthreads();
 
-    // ---------------------------------------------------------------- CLAHE: bilinear blend + LUT_OUT, in place
+    // ---------------------------------------------------------------- CLAHE: bilinear blend + LUT_OUT
     // A warp owns 32 consecutive P columns (slice rows) over a band of P rows: the vertical weight / offsets stay in
     // registers, the horizontal ones are warp-uniform reads, pixel reads and writes are conflict-free.
     {
+        uint8_t* out = p.out_clahe + s * p.out_pitch;     // a warp's 32 results are one 32-byte row segment: stored straight to global
         const int nchunk = (W + 31) >> 5;
         const int nband = 8, band_rows = (cols + nband - 1) / nband;
         for (int task = warp; task < nchunk * nband; task += kWarps) {
@@ -520,18 +521,11 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
                 uint8_t g0, g1;
                 if (use_tz && !__any_sync(amask, (v0 | v1) != 0)) { g0 = blend_bg(r); g1 = blend_bg(r + 1); }   // warp-uniform
                 else { g0 = blend(r, v0); g1 = blend(r + 1, v1); }
-                su[r * W + c] = g0;
-                su[(r + 1) * W + c] = g1;
+                out[r * W + c] = g0;
+                out[(r + 1) * W + c] = g1;
             }
-            if (r < r_end) su[r * W + c] = blend(r, su[r * W + c]);
+            if (r < r_end) out[r * W + c] = blend(r, su[r * W + c]);
         }
-    }
-    __syncthreads();
-    {
-        uint8_t* out = p.out_clahe + s * p.out_pitch;
-        uint32_t* out32 = reinterpret_cast<uint32_t*>(out);
-        for (int q = tid; q < nw; q += kThreads) out32[q] = su32[q];
-        for (int o = (nw << 2) + tid; o < npx; o += kThreads) out[o] = su[o];
     }
 }
 
