@@ -76,6 +76,24 @@ __device__ __forceinline__ int small_div(int a, int b) {
     return (int)__fmul_rn(__fdividef((float)a, (float)b), 1.000004f);
 }
 
+// Packed FP32 pairs (Blackwell FMUL2 / FADD2): two IEEE round-to-nearest operations per issue slot.  ptxas contracts a
+// mul.f32x2 feeding an add.f32x2 into FFMA2 even with -fmad=false, which would drop a rounding step, so add2 is only used
+// on operands that are not products (the exact magic-subtract conversions); sums of products stay scalar.
+__device__ __forceinline__ void mul2(float& o0, float& o1, float a0, float a1, float b0, float b1) {
+    unsigned long long a, b, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(r));
+}
+__device__ __forceinline__ void add2(float& o0, float& o1, float a0, float a1, float b0, float b1) {
+    unsigned long long a, b, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(r));
+}
+
 template <bool DO_CLAHE>
 __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -499,13 +517,15 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
                 const uint32_t h1 = *reinterpret_cast<const uint16_t*>(P1 + off);
                 const uint32_t h2 = *reinterpret_cast<const uint16_t*>(P2 + off);
                 // uint8 -> float without the conversion pipe: bits(2^23 + b) - 2^23 (PRMT builds the bits)
-                const float l11 = __fsub_rn(__uint_as_float(__byte_perm(h1, 0x4b000000u, 0x7540)), 8388608.0f);
-                const float l12 = __fsub_rn(__uint_as_float(__byte_perm(h1, 0x4b000000u, 0x7541)), 8388608.0f);
-                const float l21 = __fsub_rn(__uint_as_float(__byte_perm(h2, 0x4b000000u, 0x7540)), 8388608.0f);
-                const float l22 = __fsub_rn(__uint_as_float(__byte_perm(h2, 0x4b000000u, 0x7541)), 8388608.0f);
-                const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
-                const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
-                const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+                float l11, l12, l21, l22;
+                add2(l11, l21, __uint_as_float(__byte_perm(h1, 0x4b000000u, 0x7540)), __uint_as_float(__byte_perm(h2, 0x4b000000u, 0x7540)), -8388608.0f, -8388608.0f);
+                add2(l12, l22, __uint_as_float(__byte_perm(h1, 0x4b000000u, 0x7541)), __uint_as_float(__byte_perm(h2, 0x4b000000u, 0x7541)), -8388608.0f, -8388608.0f);
+                float a1, a2, b1, b2, t1, t2;
+                mul2(a1, a2, l11, l21, xa1, xa1);
+                mul2(b1, b2, l12, l22, xa, xa);
+                const float top = __fadd_rn(a1, b1), bot = __fadd_rn(a2, b2);
+                mul2(t1, t2, top, bot, ya1, ya);
+                const float res = __fadd_rn(t1, t2);
                 // cvRound (half-even) of a value in [0, 255.0001]: the low mantissa bits of res + 1.5 * 2^23
                 return lutout[__float_as_uint(__fadd_rn(res, 12582912.0f)) & 0xffu];
             };
@@ -513,7 +533,9 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
             // dependent chains (pixel -> pair table -> blend -> LUT_OUT) overlap
             int r = band * band_rows;
             auto blend_bg = [&](int r) -> uint8_t {
-                const float res = __fadd_rn(__fmul_rn(tz1[r], ya1), __fmul_rn(tz2[r], ya));
+                float t1, t2;
+                mul2(t1, t2, tz1[r], tz2[r], ya1, ya);
+                const float res = __fadd_rn(t1, t2);
                 return lutout[__float_as_uint(__fadd_rn(res, 12582912.0f)) & 0xffu];
             };
             for (; r + 1 < r_end; r += 2) {
