@@ -31,6 +31,19 @@ void set_error(const char* fmt, ...);
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// Packed FP32 pairs (Blackwell FADD2 / FMUL2 / FFMA2): two IEEE operations per issue slot, each half rounded exactly like
+// the scalar instruction.  CAUTION: ptxas contracts a mul2 that feeds an add2 into one FFMA2 even under -fmad=false (one
+// rounding instead of two).  Where the reference rounds the product and the sum separately, keep the sum scalar or make
+// sure (cuobjdump -sass) that the pattern did not fuse.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 pk2(float2 v) { return pk2(v.x, v.y); }
+__device__ __forceinline__ float2 upk2(f32x2 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ f32x2 mul2_rn(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2_rn(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 sub2_rn(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2_rn(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 // Order-preserving float <-> uint32 key (so unsigned atomicMin/atomicMax order floats).
 __device__ __forceinline__ unsigned f2key(float f) {
     unsigned b = __float_as_uint(f);
