@@ -325,6 +325,30 @@ def test_recon_duplicates_sparse_and_empty(ops, torch_mod, cuda_device):
     assert int(empty.sum()) == 0
 
 
+@pytest.mark.parametrize("shape_xyz", [(182, 30, 26), (64, 20, 18), (66, 22, 12), (130, 10, 7), (24, 9, 10), (21, 14, 10)])
+def test_recon_shapes_and_spread_indices(ops, torch_mod, cuda_device, shape_xyz):
+    """Row lengths of 0 and 2 (mod 4), odd sizes (byte fallback), slice sets that span several 64-wide chunks, two
+    volumes with different present ranges, uint8 and float32 volumes."""
+    torch = torch_mod
+    X, Y, Z = shape_xyz
+    rng = np.random.default_rng(X * 1000 + Y)
+    for plano in PLANOS:
+        n_p, rows, cols = ops.plane_dims(plano, X, Y, Z)
+        idx0 = sorted(set(int(i) for i in rng.choice(n_p, size=max(1, n_p // 3), replace=False)))
+        idx1 = [n_p - 1] if n_p > 1 else [0]
+        vols_of = [0] * len(idx0) + [1] * len(idx1)
+        idx = idx0 + idx1
+        sl = ((rng.random((len(idx), rows, cols)) < 0.4) * rng.integers(1, 256, size=(len(idx), rows, cols))).astype(np.uint8)
+        want0 = O.reconstruir(list(sl[:len(idx0)]), idx0, (X, Y, Z), plano).transpose(2, 1, 0).astype(np.uint8)
+        want1 = O.reconstruir(list(sl[len(idx0):]), idx1, (X, Y, Z), plano).transpose(2, 1, 0).astype(np.uint8)
+        dev = torch.from_numpy(sl).to(cuda_device)
+        for dtype in (torch.uint8, torch.float32):
+            got = ops.recon(dev, vols_of, idx, plano, 3, (X, Y, Z), dtype=dtype)
+            assert np.array_equal(got[0].cpu().numpy().astype(np.uint8), want0), (shape_xyz, plano, dtype)
+            assert np.array_equal(got[1].cpu().numpy().astype(np.uint8), want1), (shape_xyz, plano, dtype)
+            assert float(got[2].abs().sum()) == 0.0
+
+
 def test_no_cpu_fallback(ops, torch_mod):
     torch = torch_mod
     with pytest.raises(TypeError):

@@ -149,6 +149,180 @@ __global__ void __launch_bounds__(256) recon_sagital_kernel(const ReconArgs a) {
     }
 }
 
+// ---- word-granular versions (uint8 volumes, even X, 4-byte aligned slices): the kernels above remain the fallback.
+// Volume rows are X bytes long; with X == 2 (mod 4) every other row starts at 2 (mod 4), so a row (or a span of it) is
+// written as [16-bit head] + aligned 32-bit words + [16-bit tail].
+// (byte != 0) -> 1 for the four bytes of a word
+__device__ __forceinline__ uint32_t nonzero_bytes01(uint32_t v) {
+    return ((((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) >> 7) & 0x01010101u;
+}
+// Task k of a span of `len` bytes (even) whose first byte sits at address parity `a2` (0 or 2): k < nfull -> aligned word
+// at byte a2 + 4k; the two tasks behind the words are the 16-bit head (bytes 0..1, only if a2) and tail.
+struct SpanTask { int off, bytes; };       // bytes: 4, 2 or 0 (nothing to do)
+__device__ __forceinline__ SpanTask span_task(int k, int len, int a2) {
+    const int body = len - a2, nfull = body >> 2;
+    SpanTask t;
+    if (k < nfull) { t.off = a2 + 4 * k; t.bytes = 4; }
+    else if (k == nfull) { t.off = 0; t.bytes = a2 ? 2 : 0; }
+    else if (k == nfull + 1) { t.off = a2 + 4 * nfull; t.bytes = (body & 2) ? 2 : 0; }
+    else { t.off = 0; t.bytes = 0; }
+    return t;
+}
+
+// Axial / coronal, one CTA per present slice: the slice is copied to shared memory with 32-bit loads, then every thread
+// gathers the four bytes Q[x .. x+3][w] of one output word (a byte transpose), binarises them and stores the word.
+__global__ void __launch_bounds__(256) recon_rows_v2_kernel(const ReconArgs a) {
+    extern __shared__ __align__(16) uint8_t T[];          // the slice as it is: Q[x][w], w fastest
+    const int X = a.X, Y = a.Y, Z = a.Z;
+    const int s = blockIdx.x;
+    const int v = a.vol_of_slice[s], idx = a.idx_of_slice[s];
+    const int n_plane = a.plano == MSL_AXIAL ? Z : Y;
+    if (v < 0 || v >= a.nvol || idx < 0 || idx >= n_plane) return;
+    if (a.slot_of[(size_t)v * n_plane + idx] != s) return;          // superseded duplicate
+    const int W = a.plano == MSL_AXIAL ? Y : Z;           // slice row length, number of output rows
+    const int tid = threadIdx.x;
+    // The copy keeps the slice's alignment (mod 16) so that the body moves as 128-bit vectors on both sides.
+    const uint8_t* src = a.slices + (size_t)s * a.slice_pitch;
+    const int shift = (int)(reinterpret_cast<uintptr_t>(src) & 15);      // multiple of 4
+    uint8_t* Q = T + shift;
+    {
+        const int nbytes = X * W;                         // multiple of 4 (checked by the launcher)
+        const int headb = min(nbytes, (16 - shift) & 15);
+        const int nvec = (nbytes - headb) >> 4;
+        const uint4* src4 = reinterpret_cast<const uint4*>(src + headb);
+        uint4* dst4 = reinterpret_cast<uint4*>(Q + headb);
+        int q = tid;
+        for (; q + 3 * 256 < nvec; q += 4 * 256) {        // four independent 128-bit loads in flight
+            const uint4 v0 = __ldg(src4 + q), v1 = __ldg(src4 + q + 256), v2 = __ldg(src4 + q + 512), v3 = __ldg(src4 + q + 768);
+            dst4[q] = v0; dst4[q + 256] = v1; dst4[q + 512] = v2; dst4[q + 768] = v3;
+        }
+        for (; q < nvec; q += 256) dst4[q] = __ldg(src4 + q);
+        const int tailb = headb + (nvec << 4);
+        for (int o = 4 * tid; o < headb; o += 4 * 256) *reinterpret_cast<uint32_t*>(Q + o) = __ldg(reinterpret_cast<const uint32_t*>(src + o));
+        for (int o = tailb + 4 * tid; o < nbytes; o += 4 * 256) *reinterpret_cast<uint32_t*>(Q + o) = __ldg(reinterpret_cast<const uint32_t*>(src + o));
+    }
+    __syncthreads();
+    const int nt = (X >> 2) + 2;                          // tasks per output row: words + head + tail
+    const unsigned magic = (unsigned)(0x100000000ull / (unsigned)nt) + 1u;
+    for (int t = tid; t < W * nt; t += 256) {
+        const int w = (int)__umulhi((unsigned)t, magic), k = t - w * nt;
+        const size_t off = a.plano == MSL_AXIAL ? (((size_t)v * Z + idx) * Y + w) * X : (((size_t)v * Z + w) * Y + idx) * X;
+        uint8_t* row = a.vol_u8 + off;
+        const SpanTask st = span_task(k, X, (int)(reinterpret_cast<uintptr_t>(row) & 2));
+        if (st.bytes == 0) continue;
+        const uint8_t* q = Q + st.off * W + w;
+        uint32_t u = (uint32_t)q[0] | ((uint32_t)q[W] << 8);
+        if (st.bytes == 4) {
+            u |= ((uint32_t)q[2 * W] << 16) | ((uint32_t)q[3 * W] << 24);
+            *reinterpret_cast<uint32_t*>(row + st.off) = nonzero_bytes01(u);
+        } else {
+            *reinterpret_cast<uint16_t*>(row + st.off) = (uint16_t)nonzero_bytes01(u);
+        }
+    }
+}
+
+// Sagital: out[v][z][y][x] = Q_x[y][z] - the slice index is the volume's FASTEST axis, so a present slice contributes one
+// byte to every row of the volume.  Scattering those bytes (or 40-byte fragments of them) costs a read-modify-write per
+// 32-byte sector, so this kernel writes the volume DENSELY instead (and the launcher skips the memset): one CTA per
+// (2 slice rows y0, y0+1; volume) assembles, for every z, the 2 * X contiguous output bytes out[z][y0 .. y0+1][0 .. X) in
+// shared memory - zeros, then the bytes of the present slices, transposed on the way in (only ~20 % of the indices are
+// present) - and streams them out as aligned 32-bit words.  grid (ceil(Y / 2), nvol); block 512;
+// smem Z * pitch + 32 + (2 X + 1) * 4 bytes.
+constexpr int kSagRows = 2;
+constexpr int kSagThreads = 512;
+constexpr int kSagWarps = kSagThreads / 32;
+constexpr int kSagBatch = 8;                              // 32-bit loads in flight per lane
+__global__ void __launch_bounds__(kSagThreads) recon_sagital_dense_kernel(const ReconArgs a, int pitch) {
+    extern __shared__ __align__(16) uint8_t Sraw[];
+    const int X = a.X, Y = a.Y, Z = a.Z;
+    const int y0 = blockIdx.x * kSagRows, v = blockIdx.y;
+    // [Z][pitch]: byte c = yy * X + x of the chunk of plane z; same alignment (mod 16) as the chunk's place in the volume
+    uint8_t* S = Sraw + (reinterpret_cast<uintptr_t>(a.vol_u8 + (((size_t)v * Z) * Y + y0) * X) & 15);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ny = min(kSagRows, Y - y0);
+    const int chunk = ny * X;                             // bytes per z, a multiple of 4 (launcher)
+    int32_t* s_px = reinterpret_cast<int32_t*>(Sraw + (((size_t)Z * pitch + 16 + 15) & ~(size_t)15));   // [X] present slice indices
+    int32_t* s_ps = s_px + X;                             // [X] their slots, [X] the count
+    {
+        uint4* s4 = reinterpret_cast<uint4*>(Sraw);
+        const int n4 = (Z * pitch + 16 + 15) >> 4;        // the launcher's allocation is rounded up to 16 bytes
+        for (int q = tid; q < n4; q += kSagThreads) s4[q] = make_uint4(0, 0, 0, 0);
+    }
+    if (warp == 0) {                                      // compact list of the present slices
+        int cnt = 0;
+        for (int xb = 0; xb < X; xb += 32) {
+            const int x = xb + lane;
+            const int slot = x < X ? a.slot_of[(size_t)v * X + x] : -1;
+            const unsigned m = __ballot_sync(FULL, slot >= 0);
+            if (slot >= 0) { const int i = cnt + __popc(m & ((1u << lane) - 1u)); s_px[i] = x; s_ps[i] = slot; }
+            cnt += __popc(m);
+        }
+        if (lane == 0) s_ps[X] = cnt;
+    }
+    __syncthreads();
+    // present slices: ny * Z contiguous bytes each, read as 32-bit words (task = slice x group of 32 words, warp-uniform
+    // slice base, kSagBatch loads per lane in flight).  S is zero-filled and lesion masks are sparse, so only non-zero
+    // words cost anything beyond the load (the branch is warp-uniform almost everywhere).
+    {
+        const int nwz = (ny * Z) >> 2;                    // ny * Z is a multiple of 4 (launcher)
+        const int ngrp = (nwz + 31) >> 5, ntask = s_ps[X] * ngrp;
+        const unsigned magic_g = (unsigned)(0x100000000ull / (unsigned)ngrp) + 1u;
+        const uint8_t* base = a.slices + (size_t)y0 * Z;
+        for (int k0 = warp; k0 < ntask; k0 += kSagBatch * kSagWarps) {
+            uint32_t u[kSagBatch], meta[kSagBatch];
+#pragma unroll
+            for (int i = 0; i < kSagBatch; ++i) {
+                const int k = k0 + kSagWarps * i;
+                u[i] = 0; meta[i] = 0;
+                if (k < ntask) {
+                    const int xi = ngrp == 1 ? k : (int)__umulhi((unsigned)k, magic_g), w = (k - xi * ngrp) * 32 + lane;
+                    if (w < nwz) {
+                        u[i] = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)s_ps[xi] * a.slice_pitch) + w);
+                        meta[i] = (uint32_t)w | ((uint32_t)s_px[xi] << 16);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kSagBatch; ++i)
+                if (u[i]) {
+                    const int x = (int)(meta[i] >> 16);
+                    int b = 4 * (int)(meta[i] & 0xffffu);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j, ++b)
+                        if ((u[i] >> (8 * j)) & 0xffu) { const int yy = b >= Z ? 1 : 0; S[(b - yy * Z) * pitch + yy * X + x] = 1; }
+                }
+        }
+    }
+    __syncthreads();
+    // stream out: the chunk of plane z starts at the same offset (mod 16) in shared memory and in the volume (the launcher
+    // picks pitch == Y * X (mod 16), the kernel shifts S by the alignment of the first chunk), so its body moves as
+    // 128-bit vectors; a warp per plane, the lanes behind the vectors take the unaligned head / tail words.
+    uint8_t* out = a.vol_u8 + (((size_t)v * Z) * Y + y0) * X;
+    const size_t zstride = (size_t)Y * X;
+    uint8_t* g = out + warp * zstride;
+    const uint8_t* sm = S + warp * pitch;
+    // kSagWarps * zstride == 0 (mod 16): the head / body / tail split of a warp's planes never changes
+    const int headb = min(chunk, (int)((16 - (reinterpret_cast<uintptr_t>(g) & 15)) & 15));
+    const int nvec = (chunk - headb) >> 4, tailb = headb + 16 * nvec;
+    const int nhead = headb >> 2, ntail = (chunk - tailb) >> 2;
+    const int e = 31 - lane;                              // lanes 31, 30, ... : head words, then tail words
+    const int woff = e < nhead ? 4 * e : (e - nhead < ntail ? tailb + 4 * (e - nhead) : -1);
+    if (nvec <= 32) {
+        const int voff = lane < nvec ? headb + 16 * lane : -1;
+        for (int z = warp; z < Z; z += kSagWarps, g += kSagWarps * zstride, sm += kSagWarps * pitch) {
+            if (voff >= 0) *reinterpret_cast<uint4*>(g + voff) = *reinterpret_cast<const uint4*>(sm + voff);
+            if (woff >= 0) *reinterpret_cast<uint32_t*>(g + woff) = *reinterpret_cast<const uint32_t*>(sm + woff);
+        }
+    } else {
+        for (int z = warp; z < Z; z += kSagWarps, g += kSagWarps * zstride, sm += kSagWarps * pitch) {
+#pragma unroll 1
+            for (int q = lane; q < nvec; q += 32)
+                *reinterpret_cast<uint4*>(g + headb + 16 * q) = *reinterpret_cast<const uint4*>(sm + headb + 16 * q);
+            if (woff >= 0) *reinterpret_cast<uint32_t*>(g + woff) = *reinterpret_cast<const uint32_t*>(sm + woff);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ vote + counts
 // bit 7 of each byte set iff that byte == 0 (exact, no cross-byte borrow)
 __device__ __forceinline__ uint32_t zero_bytes(uint32_t v) {
@@ -370,7 +544,21 @@ int launch_recon(const uint8_t* slices, size_t slice_pitch, const int32_t* vol_o
     const size_t nmap = (size_t)nvol * n_plane;
     const size_t N = (size_t)nvol * X * Y * Z;
     int32_t* xrange = slot_of + nmap;                     // [nvol][2] first / last present index
-    if (vol_u8) MSL_CUDA_CHECK(cudaMemsetAsync(vol_u8, 0, N, stream));
+    // word-granular kernels: uint8 volumes, even X, 4-byte aligned slices whose size is a multiple of 4
+    const bool words = nslices > 0 && vol_u8 && !vol_f32 && (X & 1) == 0 && (((size_t)X * Y * Z) < 0x7fffffffull) &&
+                       ((slice_pitch | reinterpret_cast<uintptr_t>(slices)) & 3) == 0;
+    // dense sagital kernel: every byte of the volume is written by the kernel itself, no memset
+    int sag_pitch = 0;
+    size_t sag_smem = 0;
+    bool sag_dense = words && plano == MSL_SAGITAL && (Z & 1) == 0 && X < 65536 && (size_t)kSagRows * Z < 4 * 65536 && ((size_t)X * Y) % 4 == 0 && (reinterpret_cast<uintptr_t>(vol_u8) & 3) == 0 &&
+                     (Y % kSagRows == 0 || X % 4 == 0);
+    if (sag_dense) {
+        sag_pitch = kSagRows * X;                         // multiple of 4, and == Y * X (mod 16): see the kernel's stream-out
+        sag_pitch += (int)(((size_t)X * Y - (size_t)sag_pitch) & 15);
+        sag_smem = (((size_t)Z * sag_pitch + 16 + 15) & ~(size_t)15) + (size_t)(2 * X + 1) * sizeof(int32_t);
+        if (sag_smem > 227 * 1024) sag_dense = false;
+    }
+    if (vol_u8 && !sag_dense) MSL_CUDA_CHECK(cudaMemsetAsync(vol_u8, 0, N, stream));
     if (vol_f32) MSL_CUDA_CHECK(cudaMemsetAsync(vol_f32, 0, N * sizeof(float), stream));
     if (nslices <= 0) return MSL_OK;
     {
@@ -388,6 +576,23 @@ int launch_recon(const uint8_t* slices, size_t slice_pitch, const int32_t* vol_o
     a.slot_of = slot_of; a.xrange = xrange; a.vol_u8 = vol_u8; a.vol_f32 = vol_f32;
     a.X = X; a.Y = Y; a.Z = Z; a.plano = plano; a.nvol = nvol;
     ProfScope prof(K_RECON_GATHER, stream);
+    if (sag_dense) {
+        MSL_CUDA_CHECK(cudaFuncSetAttribute(recon_sagital_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sag_smem));
+        dim3 grid((Y + kSagRows - 1) / kSagRows, nvol);
+        recon_sagital_dense_kernel<<<grid, kSagThreads, sag_smem, stream>>>(a, sag_pitch);
+        MSL_LAUNCH_CHECK("recon_sagital_dense_kernel");
+        return MSL_OK;
+    }
+    if (words && plano != MSL_SAGITAL && (reinterpret_cast<uintptr_t>(vol_u8) & 1) == 0) {
+        const int W = plano == MSL_AXIAL ? Y : Z;
+        const size_t smem = (size_t)X * W + 16;
+        if (((size_t)X * W) % 4 == 0 && smem <= 227 * 1024) {
+            MSL_CUDA_CHECK(cudaFuncSetAttribute(recon_rows_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            recon_rows_v2_kernel<<<nslices, 256, smem, stream>>>(a);
+            MSL_LAUNCH_CHECK("recon_rows_v2_kernel");
+            return MSL_OK;
+        }
+    }
     if (plano == MSL_SAGITAL) {
         dim3 grid((Z + kTile - 1) / kTile, Y, nvol);
         recon_sagital_kernel<<<grid, 256, 0, stream>>>(a);
