@@ -149,30 +149,17 @@ __global__ void __launch_bounds__(256) recon_sagital_kernel(const ReconArgs a) {
     }
 }
 
-// ---- word-granular versions (uint8 volumes, even X, 4-byte aligned slices): the kernels above remain the fallback.
-// Volume rows are X bytes long; with X == 2 (mod 4) every other row starts at 2 (mod 4), so a row (or a span of it) is
-// written as [16-bit head] + aligned 32-bit words + [16-bit tail].
-// (byte != 0) -> 1 for the four bytes of a word
-__device__ __forceinline__ uint32_t nonzero_bytes01(uint32_t v) {
-    return ((((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) >> 7) & 0x01010101u;
-}
-// Task k of a span of `len` bytes (even) whose first byte sits at address parity `a2` (0 or 2): k < nfull -> aligned word
-// at byte a2 + 4k; the two tasks behind the words are the 16-bit head (bytes 0..1, only if a2) and tail.
-struct SpanTask { int off, bytes; };       // bytes: 4, 2 or 0 (nothing to do)
-__device__ __forceinline__ SpanTask span_task(int k, int len, int a2) {
-    const int body = len - a2, nfull = body >> 2;
-    SpanTask t;
-    if (k < nfull) { t.off = a2 + 4 * k; t.bytes = 4; }
-    else if (k == nfull) { t.off = 0; t.bytes = a2 ? 2 : 0; }
-    else if (k == nfull + 1) { t.off = a2 + 4 * nfull; t.bytes = (body & 2) ? 2 : 0; }
-    else { t.off = 0; t.bytes = 0; }
-    return t;
-}
+// ---- sparse-scatter versions (uint8 volumes, even X, 4-byte aligned slices): the kernels above remain the fallback.
+// Lesion masks are almost empty, and a transposed copy of a slice costs ~10 instructions per byte however it is done.
+// So the transposed slice is ASSEMBLED in zero-filled shared memory - the slice is scanned with 128-bit loads and only
+// its non-zero bytes are scattered - and then streamed to the volume with 128-bit stores.
 
-// Axial / coronal, one CTA per present slice: the slice is copied to shared memory with 32-bit loads, then every thread
-// gathers the four bytes Q[x .. x+3][w] of one output word (a byte transpose), binarises them and stores the word.
-__global__ void __launch_bounds__(256) recon_rows_v2_kernel(const ReconArgs a) {
-    extern __shared__ __align__(16) uint8_t T[];          // the slice as it is: Q[x][w], w fastest
+// Axial / coronal, one CTA per present slice Q[x][w] (w = y for axial, z for coronal; w fastest):
+//   axial   slice k: out[v][k][w][0 .. X)     coronal slice j: out[v][w][j][0 .. X)
+// Output row w lives at T2 + w * pitch with pitch == (global row stride) (mod 16) and T2 shifted by the alignment of row 0,
+// so every row has the same 16-byte phase in shared memory and in the volume: [16-bit head] + 128-bit body + [16-bit tail].
+__global__ void __launch_bounds__(256) recon_rows_sparse_kernel(const ReconArgs a, int pitch) {
+    extern __shared__ __align__(16) uint8_t Traw[];
     const int X = a.X, Y = a.Y, Z = a.Z;
     const int s = blockIdx.x;
     const int v = a.vol_of_slice[s], idx = a.idx_of_slice[s];
@@ -180,44 +167,65 @@ __global__ void __launch_bounds__(256) recon_rows_v2_kernel(const ReconArgs a) {
     if (v < 0 || v >= a.nvol || idx < 0 || idx >= n_plane) return;
     if (a.slot_of[(size_t)v * n_plane + idx] != s) return;          // superseded duplicate
     const int W = a.plano == MSL_AXIAL ? Y : Z;           // slice row length, number of output rows
-    const int tid = threadIdx.x;
-    // The copy keeps the slice's alignment (mod 16) so that the body moves as 128-bit vectors on both sides.
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t row0 = a.plano == MSL_AXIAL ? (((size_t)v * Z + idx) * Y) * X : (((size_t)v * Z) * Y + idx) * X;
+    const size_t rstride = a.plano == MSL_AXIAL ? (size_t)X : (size_t)Y * X;
+    uint8_t* g0 = a.vol_u8 + row0;
+    uint8_t* T2 = Traw + (reinterpret_cast<uintptr_t>(g0) & 15);
+    // loads first (four 128-bit vectors per thread in flight), zero-fill while they are on their way
     const uint8_t* src = a.slices + (size_t)s * a.slice_pitch;
-    const int shift = (int)(reinterpret_cast<uintptr_t>(src) & 15);      // multiple of 4
-    uint8_t* Q = T + shift;
-    {
-        const int nbytes = X * W;                         // multiple of 4 (checked by the launcher)
-        const int headb = min(nbytes, (16 - shift) & 15);
-        const int nvec = (nbytes - headb) >> 4;
-        const uint4* src4 = reinterpret_cast<const uint4*>(src + headb);
-        uint4* dst4 = reinterpret_cast<uint4*>(Q + headb);
-        int q = tid;
-        for (; q + 3 * 256 < nvec; q += 4 * 256) {        // four independent 128-bit loads in flight
-            const uint4 v0 = __ldg(src4 + q), v1 = __ldg(src4 + q + 256), v2 = __ldg(src4 + q + 512), v3 = __ldg(src4 + q + 768);
-            dst4[q] = v0; dst4[q + 256] = v1; dst4[q + 512] = v2; dst4[q + 768] = v3;
+    const int nbytes = X * W;                             // multiple of 4 (launcher)
+    const int headb = min(nbytes, (int)((16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15));     // multiple of 4
+    const int nvec = (nbytes - headb) >> 4, tailb = headb + (nvec << 4);
+    const uint4* src4 = reinterpret_cast<const uint4*>(src + headb);
+    const unsigned magic_w = (unsigned)(0x100000000ull / (unsigned)W) + 1u;       // W >= 2 (even)
+    auto scatter = [&](uint32_t u, int o) {               // the four bytes at flat offset o of the slice
+        if (u == 0) return;
+        int x = (int)__umulhi((unsigned)o, magic_w), w = o - x * W;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if ((u >> (8 * j)) & 0xffu) T2[w * pitch + x] = 1;
+            if (++w == W) { w = 0; ++x; }
         }
-        for (; q < nvec; q += 256) dst4[q] = __ldg(src4 + q);
-        const int tailb = headb + (nvec << 4);
-        for (int o = 4 * tid; o < headb; o += 4 * 256) *reinterpret_cast<uint32_t*>(Q + o) = __ldg(reinterpret_cast<const uint32_t*>(src + o));
-        for (int o = tailb + 4 * tid; o < nbytes; o += 4 * 256) *reinterpret_cast<uint32_t*>(Q + o) = __ldg(reinterpret_cast<const uint32_t*>(src + o));
+    };
+    uint4 pre[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const int q = tid + 256 * i; pre[i] = q < nvec ? __ldg(src4 + q) : make_uint4(0, 0, 0, 0); }
+    {
+        uint4* t4 = reinterpret_cast<uint4*>(Traw);
+        const int n4 = (W * pitch + 16 + 15) >> 4;
+        for (int q = tid; q < n4; q += 256) t4[q] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
-    const int nt = (X >> 2) + 2;                          // tasks per output row: words + head + tail
-    const unsigned magic = (unsigned)(0x100000000ull / (unsigned)nt) + 1u;
-    for (int t = tid; t < W * nt; t += 256) {
-        const int w = (int)__umulhi((unsigned)t, magic), k = t - w * nt;
-        const size_t off = a.plano == MSL_AXIAL ? (((size_t)v * Z + idx) * Y + w) * X : (((size_t)v * Z + w) * Y + idx) * X;
-        uint8_t* row = a.vol_u8 + off;
-        const SpanTask st = span_task(k, X, (int)(reinterpret_cast<uintptr_t>(row) & 2));
-        if (st.bytes == 0) continue;
-        const uint8_t* q = Q + st.off * W + w;
-        uint32_t u = (uint32_t)q[0] | ((uint32_t)q[W] << 8);
-        if (st.bytes == 4) {
-            u |= ((uint32_t)q[2 * W] << 16) | ((uint32_t)q[3 * W] << 24);
-            *reinterpret_cast<uint32_t*>(row + st.off) = nonzero_bytes01(u);
-        } else {
-            *reinterpret_cast<uint16_t*>(row + st.off) = (uint16_t)nonzero_bytes01(u);
-        }
+    auto scan16 = [&](const uint4& u, int q) {
+        if ((u.x | u.y | u.z | u.w) == 0) return;
+        const int o = headb + 16 * q;
+        scatter(u.x, o); scatter(u.y, o + 4); scatter(u.z, o + 8); scatter(u.w, o + 12);
+    };
+#pragma unroll
+    for (int i = 0; i < 4; ++i) scan16(pre[i], tid + 256 * i);
+    for (int q0 = 4 * 256 + tid; q0 < nvec; q0 += 4 * 256) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const int q = q0 + 256 * i; pre[i] = q < nvec ? __ldg(src4 + q) : make_uint4(0, 0, 0, 0); }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) scan16(pre[i], q0 + 256 * i);
+    }
+    for (int o = 4 * tid; o < headb; o += 4 * 256) scatter(__ldg(reinterpret_cast<const uint32_t*>(src + o)), o);
+    for (int o = tailb + 4 * tid; o < nbytes; o += 4 * 256) scatter(__ldg(reinterpret_cast<const uint32_t*>(src + o)), o);
+    __syncthreads();
+    // stream out, a warp per row; 8 * rstride == 0 (mod 16), so a warp's rows all split the same way
+    uint8_t* g = g0 + warp * rstride;
+    const uint8_t* sm = T2 + warp * pitch;
+    const int hb = min(X, (int)((16 - (reinterpret_cast<uintptr_t>(g) & 15)) & 15));              // even
+    const int nv = (X - hb) >> 4, tb = hb + 16 * nv;
+    const int nhead = hb >> 1, ntail = (X - tb) >> 1;     // halfwords, <= 7 each
+    const int e = 31 - lane;                              // lanes 31, 30, ... : head halfwords, then tail halfwords
+    const int hoff = e < nhead ? 2 * e : (e - nhead < ntail ? tb + 2 * (e - nhead) : -1);
+    for (int w = warp; w < W; w += 8, g += 8 * rstride, sm += 8 * pitch) {
+#pragma unroll 1
+        for (int q = lane; q < nv; q += 32)
+            *reinterpret_cast<uint4*>(g + hb + 16 * q) = *reinterpret_cast<const uint4*>(sm + hb + 16 * q);
+        if (hoff >= 0) *reinterpret_cast<uint16_t*>(g + hoff) = *reinterpret_cast<const uint16_t*>(sm + hoff);
     }
 }
 
@@ -585,11 +593,13 @@ int launch_recon(const uint8_t* slices, size_t slice_pitch, const int32_t* vol_o
     }
     if (words && plano != MSL_SAGITAL && (reinterpret_cast<uintptr_t>(vol_u8) & 1) == 0) {
         const int W = plano == MSL_AXIAL ? Y : Z;
-        const size_t smem = (size_t)X * W + 16;
-        if (((size_t)X * W) % 4 == 0 && smem <= 227 * 1024) {
-            MSL_CUDA_CHECK(cudaFuncSetAttribute(recon_rows_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            recon_rows_v2_kernel<<<nslices, 256, smem, stream>>>(a);
-            MSL_LAUNCH_CHECK("recon_rows_v2_kernel");
+        const size_t rstride = plano == MSL_AXIAL ? (size_t)X : (size_t)X * Y;
+        const int pitch = X + (int)((rstride - (size_t)X) & 15);       // == rstride (mod 16), even
+        const size_t smem = (((size_t)W * pitch + 16 + 15) & ~(size_t)15);
+        if ((W & 1) == 0 && ((size_t)X * W) % 4 == 0 && smem <= 227 * 1024) {
+            MSL_CUDA_CHECK(cudaFuncSetAttribute(recon_rows_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            recon_rows_sparse_kernel<<<nslices, 256, smem, stream>>>(a, pitch);
+            MSL_LAUNCH_CHECK("recon_rows_sparse_kernel");
             return MSL_OK;
         }
     }
