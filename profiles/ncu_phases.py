@@ -15,8 +15,7 @@ marks = [('load + blank check', find('// ---------------------------------------
          ('fold / clip / CDF', find('CLAHE: fold u-bins into L-bins')),
          ('weight tables', find('interpolation tables (OpenCV CLAHE_Interpolation_Body)')),
          ('pair tables', find('Pair tables: PT[ty][u][j]')),
-         ('blend', find('CLAHE: bilinear blend + LUT_OUT, in place')),
-         ('copy out', find('uint8_t* out = p.out_clahe + s * p.out_pitch;')),
+         ('blend', find('CLAHE: bilinear blend + LUT_OUT')),
          ('end', 10 ** 6)]
 agg = {}
 tot_i = sum(r[0] for r in rows); tot_s = sum(r[1] for r in rows)

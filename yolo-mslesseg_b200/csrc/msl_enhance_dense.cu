@@ -240,6 +240,15 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
                 unsigned* ht = hist + (tya[c] * 8 + tx) * 256;
                 const uint8_t* px = su + r0 * W + c;
                 int r = r0;
+                for (; r + 7 < r_end; r += 8, px += 8 * W) {       // eight independent loads in flight
+                    uint32_t v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = px[i * W];
+                    if ((v[0] | v[1] | v[2] | v[3] | v[4] | v[5] | v[6] | v[7]) == 0) continue;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (v[i]) atomicAdd(&ht[v[i]], 1u);
+                }
                 for (; r + 3 < r_end; r += 4, px += 4 * W) {
                     const uint32_t v0 = px[0], v1 = px[W], v2 = px[2 * W], v3 = px[3 * W];    // loads first, atomics after
                     if ((v0 | v1 | v2 | v3) == 0) continue;
@@ -538,15 +547,30 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
                 const float res = __fadd_rn(t1, t2);
                 return lutout[__float_as_uint(__fadd_rn(res, 12582912.0f)) & 0xffu];
             };
-            for (; r + 1 < r_end; r += 2) {
-                const uint32_t v0 = su[r * W + c], v1 = su[(r + 1) * W + c];
+            uint8_t* op = out + (unsigned)(r * W + c);        // running output pointer
+            const unsigned Wu = (unsigned)W;
+            const uint8_t* ip = su + r * W + c;
+            // four rows per iteration: one vote decides whether all 32 x 4 pixels are background (the short path)
+            for (; r + 3 < r_end; r += 4, op += 4 * Wu, ip += 4 * W) {
+                const uint32_t v0 = ip[0], v1 = ip[W], v2 = ip[2 * W], v3 = ip[3 * W];
+                uint8_t g0, g1, g2, g3;
+                if (use_tz && !__any_sync(amask, (v0 | v1 | v2 | v3) != 0)) {
+                    g0 = blend_bg(r); g1 = blend_bg(r + 1); g2 = blend_bg(r + 2); g3 = blend_bg(r + 3);
+                } else {
+                    g0 = blend(r, v0); g1 = blend(r + 1, v1);
+                    g2 = blend(r + 2, v2); g3 = blend(r + 3, v3);
+                }
+                op[0] = g0; op[Wu] = g1; op[2 * Wu] = g2; op[3 * Wu] = g3;
+            }
+            for (; r + 1 < r_end; r += 2, op += 2 * Wu, ip += 2 * W) {
+                const uint32_t v0 = ip[0], v1 = ip[W];
                 uint8_t g0, g1;
                 if (use_tz && !__any_sync(amask, (v0 | v1) != 0)) { g0 = blend_bg(r); g1 = blend_bg(r + 1); }   // warp-uniform
                 else { g0 = blend(r, v0); g1 = blend(r + 1, v1); }
-                out[r * W + c] = g0;
-                out[(r + 1) * W + c] = g1;
+                op[0] = g0;
+                op[Wu] = g1;
             }
-            if (r < r_end) out[r * W + c] = blend(r, su[r * W + c]);
+            if (r < r_end) op[0] = blend(r, su[r * W + c]);
         }
     }
 }
