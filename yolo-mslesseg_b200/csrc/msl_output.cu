@@ -566,11 +566,11 @@ int launch_recon(const uint8_t* slices, size_t slice_pitch, const int32_t* vol_o
         sag_smem = (((size_t)Z * sag_pitch + 16 + 15) & ~(size_t)15) + (size_t)(2 * X + 1) * sizeof(int32_t);
         if (sag_smem > 227 * 1024) sag_dense = false;
     }
-    if (vol_u8 && !sag_dense) MSL_CUDA_CHECK(cudaMemsetAsync(vol_u8, 0, N, stream));
-    if (vol_f32) MSL_CUDA_CHECK(cudaMemsetAsync(vol_f32, 0, N * sizeof(float), stream));
-    if (nslices <= 0) return MSL_OK;
     {
-        ProfScope prof(K_RECON_FILL, stream);
+        ProfScope prof(K_RECON_FILL, stream);             // zero fill (not needed by the dense sagital kernel) + map reset
+        if (vol_u8 && !sag_dense) MSL_CUDA_CHECK(cudaMemsetAsync(vol_u8, 0, N, stream));
+        if (vol_f32) MSL_CUDA_CHECK(cudaMemsetAsync(vol_f32, 0, N * sizeof(float), stream));
+        if (nslices <= 0) return MSL_OK;
         recon_init_kernel<<<(unsigned)((nmap + 255) / 256), 256, 0, stream>>>(slot_of, nmap, xrange, nvol);
     }
     MSL_LAUNCH_CHECK("recon_init_kernel");
