@@ -138,6 +138,19 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z,
                         uint8_t* const* outs, const uint8_t* tables,
                         void* ws, size_t ws_bytes, msl_stream_t stream);
 
+/* ---- R0: YOLO instance masks -> predicted slice masks (the producer of msl_recon's input) -------
+ * Replaces combinar_predicciones (scripts/generar_predicciones.py:123-133: every instance mask > 0.5,
+ * cv2.resize INTER_NEAREST to the image shape, maximum over the instances) and normalizar_prediccion
+ * (:136-140: cv2.flip(pred.T, 1) * 255).
+ * masks: float32 [n_inst][mh][mw] (ultralytics `masks.data` of all slices, concatenated);
+ * inst_offset: int32 [nslices + 1] (device): the instances of slice s are [inst_offset[s], inst_offset[s+1]).
+ * The model saw the PNG-oriented image, (height, width) = (cols, rows).  out: uint8, dense, one image per slice:
+ *   layout MSL_OUT_P : (cols, rows), values {0, 1}    == combinar_predicciones(preds, (cols, rows))
+ *   layout MSL_OUT_G : (rows, cols), values {0, 255}  == normalizar_prediccion(combinar_predicciones(...)),
+ *                      i.e. exactly the `slices` argument of msl_recon. */
+int msl_combine_predictions(const float* masks, const int32_t* inst_offset, int nslices, int mh, int mw,
+                            int rows, int cols, int layout, uint8_t* out, msl_stream_t stream);
+
 /* ---- R1-R2: stack predicted 2-D masks back into volumes ---------------------------------------
  * Replaces cargar_y_preprocesar_imagen's binarisation (scripts/reconstruir_volumen.py:146-148),
  * insertar_corte (:179-186) and the zero-initialised volume of reconstruir_volumen (:199-213).
@@ -168,6 +181,14 @@ int msl_consensus_eval(const uint8_t* ax, const uint8_t* co, const uint8_t* sa, 
  * counts: int64 [nvol][4] = {tp, fp, fn, tn}, overwritten. */
 int msl_confusion_counts(const uint8_t* gt, const uint8_t* pred, int nvol, size_t nvox,
                          int64_t* counts, msl_stream_t stream);
+
+/* ---- R4 at slice granularity ----------------------------------------------------
+ * The counts behind the per-slice DSC of extras/visualizar_prediccion_corte.py:150-182 (seleccionar_mejor_corte:
+ * DSC(pred_slice, gt_slice) for every slice, best one wins), for ALL slices of the three planes in one pass.
+ * gt, pred: uint8 [nvol][Z][Y][X].  counts: int64 [nvol][Z + Y + X][4] = {tp, fp, fn, tn} with the same exact
+ * ==1 / ==0 predicates as msl_confusion_counts; rows [0, Z) axial, [Z, Z+Y) coronal, [Z+Y, Z+Y+X) sagital. */
+int msl_slice_counts(const uint8_t* gt, const uint8_t* pred, int nvol, int X, int Y, int Z,
+                     int64_t* counts, msl_stream_t stream);
 
 /* ---- instrumentation (not part of the reference surface) ---------------------------------------
  * msl_kernel_launches: kernels launched by this library since load (total; per kind if non-NULL,

@@ -330,6 +330,37 @@ def num_cortes_percentil(conteos: list, percentil: int = 50) -> int:
 
 
 # --------------------------------------------------------------------------------------
+# R0  YOLO instance masks -> one predicted slice mask (the producer of R1's input)
+# --------------------------------------------------------------------------------------
+
+def resize_nearest_index(dst: int, src: int) -> np.ndarray:
+    """Source index of every destination index for cv2.resize(..., interpolation=INTER_NEAREST)
+    (OpenCV imgproc/resize.cpp resizeNN: sx = min(cvFloor(x * ifx), src - 1), ifx = 1 / (dst / src) in double)."""
+    inv_scale = float(dst) / float(src)
+    ifx = 1.0 / inv_scale
+    return np.minimum(np.floor(np.arange(dst, dtype=np.float64) * ifx).astype(np.int64), src - 1)
+
+
+def combinar_predicciones(predicciones, shape) -> np.ndarray:
+    """scripts/generar_predicciones.py:123-133: OR of the instance masks (> 0.5), each resized to `shape` =
+    (height, width) with nearest-neighbour sampling.  uint8 {0, 1}, PNG orientation (the model saw the PNG)."""
+    height, width = shape
+    out = np.zeros((height, width), dtype=np.uint8)
+    for pred in predicciones:
+        pred = np.asarray(pred)
+        binary = (pred > 0.5).astype(np.uint8)
+        sy = resize_nearest_index(height, binary.shape[0])
+        sx = resize_nearest_index(width, binary.shape[1])
+        out = np.maximum(out, binary[sy][:, sx])
+    return out
+
+
+def normalizar_prediccion(pred: np.ndarray) -> np.ndarray:
+    """scripts/generar_predicciones.py:136-140: cv2.flip(pred.T, 1) * 255 -> slice orientation, {0, 255}."""
+    return (pred.T[:, ::-1] * np.uint8(255)).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------------------
 # R1 / R2  reconstruction
 # --------------------------------------------------------------------------------------
 

@@ -143,3 +143,16 @@ def test_guardar_cortes_writes_imsave_pixels(C, tmp_path):
                 want = O.imsave_rgba(O.enhance_slice(s, mejora) if mejora else s)
             assert np.array_equal(np.array(Image.open(imgs / f"P2_FLAIR_{i}.png")), want), (plano, mejora, i)
             assert np.array_equal(np.array(Image.open(masks / f"P2_{i}.png")), O.imsave_rgba(O.slice_of(gt, plano, i)))
+
+
+@pytest.mark.gpu
+def test_generar_predicciones_shim(C):
+    """compat.generar_predicciones mirrors the reference names (scripts/generar_predicciones.py:123-140)."""
+    from mslesseg_b200.compat import generar_predicciones as GP
+    from oracle.make_golden_pred import instance_masks
+    masks = instance_masks(21, 3, 160, 136, )
+    comb = GP.combinar_predicciones(list(masks), (218, 182))
+    assert comb.dtype == np.uint8 and comb.shape == (218, 182)
+    assert np.array_equal(comb, O.combinar_predicciones(list(masks), (218, 182)))
+    assert np.array_equal(GP.normalizar_prediccion(comb), O.normalizar_prediccion(comb))
+    assert int(GP.combinar_predicciones([], (218, 182)).sum()) == 0

@@ -349,6 +349,77 @@ def test_recon_shapes_and_spread_indices(ops, torch_mod, cuda_device, shape_xyz)
             assert float(got[2].abs().sum()) == 0.0
 
 
+def test_combine_predictions_golden(ops, torch_mod, cuda_device):
+    """YOLO instance masks -> predicted slice masks: bit-exact against outputs of the reference's own
+    combinar_predicciones / normalizar_prediccion (cv2.resize INTER_NEAREST, cv2.flip) frozen by oracle/make_golden_pred.py."""
+    import json, os
+    from oracle.make_golden_pred import CASES, instance_masks
+    torch = torch_mod
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_pred_v1.json")))
+    for case, (seed, n, mh, mw, h, w) in zip(g["cases"], CASES):
+        masks = instance_masks(seed, n, mh, mw)
+        dev = torch.from_numpy(masks).to(cuda_device) if n else None
+        P = ops.combine_predictions(dev, [0, n], rows=w, cols=h, layout="P",
+                                    out=torch.empty((1, h, w), dtype=torch.uint8, device=cuda_device))[0].cpu().numpy()
+        assert sha(P) == case["combined_sha"] and int(P.sum()) == case["combined_sum"], ("P", seed)
+        G = ops.combine_predictions(dev, [0, n], rows=w, cols=h, layout="G",
+                                    out=torch.empty((1, w, h), dtype=torch.uint8, device=cuda_device))[0].cpu().numpy()
+        assert sha(G) == case["normalised_sha"], ("G", seed)
+        assert np.array_equal(G, O.normalizar_prediccion(O.combinar_predicciones(list(masks), (h, w))))
+    # several slices in one call, ragged instance counts (including none), feeding recon directly
+    seed, mh, mw, h, w = 11, 160, 128, 218, 182
+    counts = [2, 0, 3, 1]
+    allm = instance_masks(seed, sum(counts), mh, mw)
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    Q = ops.combine_predictions(torch.from_numpy(allm).to(cuda_device), off, rows=w, cols=h, layout="G")
+    for i in range(len(counts)):
+        want = O.normalizar_prediccion(O.combinar_predicciones(list(allm[off[i]:off[i + 1]]), (h, w)))
+        assert np.array_equal(Q[i].cpu().numpy(), want), i
+    vol = ops.recon(Q, [0] * 4, [10, 11, 12, 13], "axial", 1, S.SHAPE_XYZ)
+    want_vol = O.reconstruir([Q[i].cpu().numpy() for i in range(4)], [10, 11, 12, 13], S.SHAPE_XYZ, "axial")
+    assert np.array_equal(vol[0].cpu().numpy(), want_vol.transpose(2, 1, 0).astype(np.uint8))
+    with pytest.raises(ValueError):
+        ops.combine_predictions(torch.from_numpy(allm).to(cuda_device), [0, 1, 99], rows=w, cols=h)
+
+
+@pytest.mark.parametrize("shape_xyz", [(182, 218, 182), (21, 14, 10), (40, 33, 27)])
+def test_slice_counts_vs_oracle(ops, torch_mod, cuda_device, shape_xyz):
+    """Per-slice confusion counts of the three planes and the best-slice selection built on them."""
+    torch = torch_mod
+    from mslesseg_b200 import metrics as M
+    X, Y, Z = shape_xyz
+    rng = np.random.default_rng(X + 7)
+    gt = np.zeros((2, Z, Y, X), dtype=np.uint8)
+    pred = np.zeros_like(gt)
+    for v in range(2):
+        for _ in range(6):
+            z, y, x = (int(rng.integers(0, d)) for d in (Z, Y, X))
+            gt[v, max(0, z - 3):z + 3, max(0, y - 4):y + 4, max(0, x - 2):x + 5] = 1
+            pred[v, max(0, z - 2):z + 4, max(0, y - 3):y + 4, max(0, x - 3):x + 4] = 1
+    pred[1, 0, 0, 0] = 7                       # a byte that is neither 0 nor 1 belongs to no count
+    gt[1, Z - 1, Y - 1, X - 1] = 3
+    got = ops.slice_counts(torch.from_numpy(gt).to(cuda_device), torch.from_numpy(pred).to(cuda_device))
+    for v in range(2):
+        gx, px = gt[v].transpose(2, 1, 0), pred[v].transpose(2, 1, 0)          # (X, Y, Z) like the reference
+        for plano in PLANOS:
+            n_p = gx.shape[O.plane_axis(plano)]
+            want = np.array([O.confusion_counts(O.slice_of(gx, plano, i), O.slice_of(px, plano, i)) for i in range(n_p)])
+            assert np.array_equal(got[plano][v].cpu().numpy(), want), (shape_xyz, v, plano)
+            # best slice: the reference's loop with its own DSC on the slices
+            best, best_dsc = None, -1.0
+            for i in range(n_p):
+                d = O.DSC(O.slice_of(px, plano, i).astype(np.float64), O.slice_of(gx, plano, i).astype(np.float64)) if v == 0 else None
+                if d is not None and d > best_dsc:
+                    best, best_dsc = i, d
+            if v == 0:
+                assert M.seleccionar_mejor_corte(got[plano][v].cpu().numpy()) == (best, best_dsc), plano
+    # a misaligned pair of views takes the byte path
+    a = torch.from_numpy(np.concatenate([np.zeros(3, np.uint8), gt.ravel()])).to(cuda_device)[3:].view(2, Z, Y, X)
+    got2 = ops.slice_counts(a, torch.from_numpy(pred).to(cuda_device))
+    for plano in PLANOS:
+        assert torch.equal(got2[plano], got[plano])
+
+
 def test_no_cpu_fallback(ops, torch_mod):
     torch = torch_mod
     with pytest.raises(TypeError):

@@ -195,3 +195,28 @@ def test_lt_table_is_slice_independent():
     assert t[0] == 0 and t[255] == 255 and t[1] == 31
     assert O.lt_table(0)[0] == 0          # blank slice: inf*0 = NaN -> 0 (only entry 0 is reachable)
     assert O.gc_table()[16] == 1 and O.gc_table()[255] == 255
+
+
+def test_prediction_postprocessing_golden():
+    """R0: combinar_predicciones / normalizar_prediccion restated vs the reference's frozen outputs."""
+    import json, os
+    from oracle.make_golden_pred import CASES, instance_masks, sha as sha_
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_pred_v1.json")))
+    assert len(g["cases"]) == len(CASES)
+    for case, (seed, n, mh, mw, h, w) in zip(g["cases"], CASES):
+        masks = instance_masks(seed, n, mh, mw)
+        comb = O.combinar_predicciones(list(masks), (h, w))
+        assert sha_(comb) == case["combined_sha"] and int(comb.sum()) == case["combined_sum"], seed
+        norm = O.normalizar_prediccion(comb)
+        assert sha_(norm) == case["normalised_sha"] and list(norm.shape) == case["normalised_shape"], seed
+
+
+def test_resize_nearest_index_matches_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    for _ in range(60):
+        sh, sw, dh, dw = (int(v) for v in rng.integers(1, 400, 4))
+        a = rng.integers(0, 2, (sh, sw)).astype(np.uint8)
+        want = cv2.resize(a, (dw, dh), interpolation=cv2.INTER_NEAREST)
+        got = a[O.resize_nearest_index(dh, sh)][:, O.resize_nearest_index(dw, sw)]
+        assert np.array_equal(got, want), (sh, sw, dh, dw)

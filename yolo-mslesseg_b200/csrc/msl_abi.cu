@@ -252,6 +252,17 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z, uint8_t
     return MSL_OK;
 }
 
+int msl_combine_predictions(const float* masks, const int32_t* inst_offset, int nslices, int mh, int mw,
+                            int rows, int cols, int layout, uint8_t* out, msl_stream_t stream) {
+    MSL_REQUIRE(nslices >= 0 && rows > 0 && cols > 0, "non-positive size");
+    MSL_REQUIRE(layout == MSL_OUT_P || layout == MSL_OUT_G, "layout %d no válido (MSL_OUT_P o MSL_OUT_G)", layout);
+    if (nslices == 0) return MSL_OK;
+    MSL_REQUIRE(inst_offset && out, "NULL inst_offset / out");
+    MSL_REQUIRE(nslices <= 65535, "at most 65535 slices per call");
+    MSL_REQUIRE(mh > 0 && mw > 0, "non-positive mask size");      // masks may be NULL when no slice has an instance
+    return launch_combine_predictions(masks, inst_offset, nslices, mh, mw, rows, cols, layout, out, (cudaStream_t)stream);
+}
+
 int msl_recon(const uint8_t* slices, size_t slice_pitch_bytes, const int32_t* vol_of_slice, const int32_t* idx_of_slice,
               int nslices, int plano, int nvol, int X, int Y, int Z, uint8_t* vol_u8, float* vol_f32,
               void* ws, size_t ws_bytes, msl_stream_t stream) {
@@ -284,6 +295,15 @@ int msl_confusion_counts(const uint8_t* gt, const uint8_t* pred, int nvol, size_
     MSL_REQUIRE(nvol > 0 && nvox > 0, "non-positive size");
     MSL_REQUIRE(nvol <= 65535, "at most 65535 volumes per call");
     return launch_confusion_counts(gt, pred, nvol, nvox, reinterpret_cast<long long*>(counts), (cudaStream_t)stream);
+}
+
+int msl_slice_counts(const uint8_t* gt, const uint8_t* pred, int nvol, int X, int Y, int Z, int64_t* counts, msl_stream_t stream) {
+    MSL_REQUIRE(gt && pred && counts, "NULL pointer");
+    MSL_REQUIRE(nvol > 0 && X > 0 && Y > 0 && Z > 0, "non-positive size");
+    MSL_REQUIRE(nvol <= 65535, "at most 65535 volumes per call");
+    MSL_REQUIRE((unsigned long long)X * Y * Z < 0xffff0000ull, "volume of %d x %d x %d voxels too large", X, Y, Z);
+    MSL_REQUIRE((size_t)(X + Y + Z) * 16 <= 200 * 1024, "too many slices for the shared-memory counters");
+    return launch_slice_counts(gt, pred, nvol, X, Y, Z, reinterpret_cast<long long*>(counts), (cudaStream_t)stream);
 }
 
 }  // extern "C"

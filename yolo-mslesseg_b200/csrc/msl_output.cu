@@ -17,6 +17,53 @@ namespace msl {
 
 namespace {
 
+// ------------------------------------------------------------------------------------ combine predictions
+// P[r][c] = OR_i (mask_i[sy(r)][sx(c)] > 0.5), (height, width) = (cols, rows); cv2.resize INTER_NEAREST picks
+// sx = min(floor(c * ifx), mw - 1) with ifx = 1 / (width / mw) evaluated in double (OpenCV resizeNN), same for y.
+// grid (tiles_c, tiles_r, nslices); block 256 = 32 (c) x 8; a CTA covers 32 x 32 pixels of P.  For the slice-oriented
+// layout G[a][b] = 255 * P[cols-1-b][a] the tile is transposed through shared memory so both sides stay coalesced.
+__global__ void __launch_bounds__(256) combine_predictions_kernel(const float* __restrict__ masks, const int32_t* __restrict__ inst_offset,
+                                                                  int mh, int mw, int rows, int cols, int layout,
+                                                                  uint8_t* __restrict__ out) {
+    __shared__ uint8_t tile[32][33];
+    __shared__ int s_sx[32], s_sy[32];
+    const int H = cols, Wd = rows;                        // P is H x Wd
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32, s = blockIdx.z;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (threadIdx.x < 32) {
+        const double ifx = 1.0 / ((double)Wd / (double)mw);
+        s_sx[threadIdx.x] = min((int)floor((double)(c0 + threadIdx.x) * ifx), mw - 1);
+    } else if (threadIdx.x < 64) {
+        const double ify = 1.0 / ((double)H / (double)mh);
+        s_sy[threadIdx.x - 32] = min((int)floor((double)(r0 + threadIdx.x - 32) * ify), mh - 1);
+    }
+    __syncthreads();
+    const int i0 = inst_offset[s], i1 = inst_offset[s + 1];
+    const size_t msz = (size_t)mh * mw;
+    const int c = c0 + tx;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int rl = ty + 8 * k, r = r0 + rl;
+        uint8_t v = 0;
+        if (r < H && c < Wd) {
+            const float* m = masks + (size_t)i0 * msz + (size_t)s_sy[rl] * mw + s_sx[tx];
+            for (int i = i0; i < i1; ++i, m += msz)
+                if (__ldg(m) > 0.5f) { v = 1; break; }
+        }
+        if (layout == MSL_OUT_P) { if (r < H && c < Wd) out[((size_t)s * H + r) * Wd + c] = v; }
+        else tile[rl][tx] = v;
+    }
+    if (layout == MSL_OUT_P) return;
+    __syncthreads();
+    // G[a][b], a = c (rows), b = cols - 1 - r: lanes run along b (descending r)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int cl = ty + 8 * k, a = c0 + cl;
+        const int r = r0 + 31 - tx;                       // lane 0 takes the tile's last P row = the smallest b
+        if (a < Wd && r < H) out[((size_t)s * rows + a) * cols + (cols - 1 - r)] = tile[31 - tx][cl] ? 255 : 0;
+    }
+}
+
 // ------------------------------------------------------------------------------------ recon
 // Volumes are zero-filled by cudaMemsetAsync; only the slices that exist are written (typically ~20 % of the
 // indices of a plane: Paciente.indices_a_usar keeps a central window of the lesion slices).
@@ -531,6 +578,83 @@ __global__ void __launch_bounds__(kCntThreads) confusion_counts_kernel(const uin
     flush_counts<1>(c, counts + (size_t)v * 4);
 }
 
+// Per-slice counts of the three planes in one flat scan.  Masks are ~99 % zeros: a 16-byte vector of gt | pred that is
+// zero costs two loads and an OR; every other voxel is classified (tp / fp / fn / neither-0-nor-1) and added to
+// shared-memory counters of its three slices, which the CTA flushes once.  tn follows from the slice size.
+// grid (ceil(nvec / (8 * kCntThreads)), nvol); dynamic smem (Z + Y + X) * 4 ints; counts pre-zeroed.
+constexpr int kSliceVecs = 8;
+__global__ void __launch_bounds__(kCntThreads) slice_counts_kernel(const uint8_t* __restrict__ gt, const uint8_t* __restrict__ pred,
+                                                                   unsigned nvox, int X, int Y, int Z, long long* __restrict__ counts) {
+    extern __shared__ int s_cnt[];           // [Z + Y + X][4]: tp, fp, fn, other
+    const int v = blockIdx.y, nsl = Z + Y + X;
+    const uint8_t* pg = gt + (size_t)v * nvox;
+    const uint8_t* pp = pred + (size_t)v * nvox;
+    for (int i = threadIdx.x; i < nsl * 4; i += kCntThreads) s_cnt[i] = 0;
+    __syncthreads();
+    const unsigned npl = (unsigned)X * (unsigned)Y;
+    bool any = false;
+    auto voxel = [&](uint32_t g, uint32_t p, unsigned z, unsigned y, unsigned x) {
+        const int k = (g == 1 && p == 1) ? 0 : (g == 0 && p == 1) ? 1 : (g == 1 && p == 0) ? 2 : 3;
+        atomicAdd(&s_cnt[4 * z + k], 1);
+        atomicAdd(&s_cnt[4 * (Z + y) + k], 1);
+        atomicAdd(&s_cnt[4 * (Z + Y + x) + k], 1);
+    };
+    // bytes [o, o + n) of the volume, n <= 16
+    auto scan = [&](const uint32_t (&wg)[4], const uint32_t (&wp)[4], unsigned o, int n) {
+        unsigned z = o / npl, r = o - z * npl, y = r / (unsigned)X, x = r - y * (unsigned)X;
+        any = true;
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) {
+            const uint32_t g = (wg[i >> 2] >> (8 * (i & 3))) & 0xffu, p = (wp[i >> 2] >> (8 * (i & 3))) & 0xffu;
+            if (g | p) voxel(g, p, z, y, x);
+            if (++x == (unsigned)X) { x = 0; if (++y == (unsigned)Y) { y = 0; ++z; } }
+        }
+    };
+    // both volumes share the alignment of the vector body only if their bases agree (mod 16); otherwise bytes
+    const bool vec = ((reinterpret_cast<uintptr_t>(pg) ^ reinterpret_cast<uintptr_t>(pp)) & 15) == 0;
+    const unsigned head = vec ? min(nvox, (unsigned)((16 - (reinterpret_cast<uintptr_t>(pg) & 15)) & 15)) : nvox;
+    const unsigned nvec = (nvox - head) / 16;
+    if (vec) {
+        const uint4* g4 = reinterpret_cast<const uint4*>(pg + head);
+        const uint4* p4 = reinterpret_cast<const uint4*>(pp + head);
+        const unsigned q0 = blockIdx.x * (unsigned)(kSliceVecs * kCntThreads) + threadIdx.x;
+        uint4 a[kSliceVecs], b[kSliceVecs];
+#pragma unroll
+        for (int j = 0; j < kSliceVecs; ++j) {
+            const unsigned q = q0 + j * kCntThreads;
+            a[j] = q < nvec ? __ldg(g4 + q) : make_uint4(0, 0, 0, 0);
+            b[j] = q < nvec ? __ldg(p4 + q) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < kSliceVecs; ++j)
+            if (a[j].x | a[j].y | a[j].z | a[j].w | b[j].x | b[j].y | b[j].z | b[j].w) {
+                const uint32_t wg[4] = {a[j].x, a[j].y, a[j].z, a[j].w}, wp[4] = {b[j].x, b[j].y, b[j].z, b[j].w};
+                scan(wg, wp, head + (q0 + j * kCntThreads) * 16, 16);
+            }
+    }
+    if (blockIdx.x == 0) {                   // unaligned head and tail (or everything, if the bases disagree mod 16)
+        for (unsigned o = threadIdx.x; o < head; o += kCntThreads)
+            if (pg[o] | pp[o]) { const uint32_t wg[4] = {pg[o], 0, 0, 0}, wp[4] = {pp[o], 0, 0, 0}; scan(wg, wp, o, 1); }
+        for (unsigned o = head + nvec * 16 + threadIdx.x; o < nvox; o += kCntThreads)
+            if (pg[o] | pp[o]) { const uint32_t wg[4] = {pg[o], 0, 0, 0}, wp[4] = {pp[o], 0, 0, 0}; scan(wg, wp, o, 1); }
+    }
+    if (!__syncthreads_or(any)) return;
+    long long* dst = counts + (size_t)v * nsl * 4;
+    for (int i = threadIdx.x; i < nsl * 4; i += kCntThreads)
+        if (s_cnt[i]) atomicAdd(reinterpret_cast<unsigned long long*>(dst) + i, (unsigned long long)s_cnt[i]);
+}
+
+// slot 3 holds the voxels that are neither 0 nor 1 in one of the masks: tn = slice size - tp - fp - fn - other
+__global__ void slice_counts_finalize_kernel(long long* counts, int nvol, int X, int Y, int Z) {
+    const int nsl = Z + Y + X;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nvol * nsl) return;
+    const int sidx = (int)(i % nsl);
+    const long long n = sidx < Z ? (long long)X * Y : (sidx < Z + Y ? (long long)X * Z : (long long)Y * Z);
+    long long* c = counts + i * 4;
+    c[3] = n - c[0] - c[1] - c[2] - c[3];
+}
+
 inline bool aligned8(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
 
 inline int chunks_for(size_t nvox, int nvol) {
@@ -620,6 +744,32 @@ int launch_recon(const uint8_t* slices, size_t slice_pitch, const int32_t* vol_o
         }
     }
     MSL_LAUNCH_CHECK("recon kernel");
+    return MSL_OK;
+}
+
+int launch_combine_predictions(const float* masks, const int32_t* inst_offset, int nslices, int mh, int mw, int rows, int cols,
+                               int layout, uint8_t* out, cudaStream_t stream) {
+    dim3 grid((rows + 31) / 32, (cols + 31) / 32, nslices);
+    ProfScope prof(K_COMBINE_PRED, stream);
+    combine_predictions_kernel<<<grid, 256, 0, stream>>>(masks, inst_offset, mh, mw, rows, cols, layout, out);
+    MSL_LAUNCH_CHECK("combine_predictions_kernel");
+    return MSL_OK;
+}
+
+int launch_slice_counts(const uint8_t* gt, const uint8_t* pred, int nvol, int X, int Y, int Z, long long* counts, cudaStream_t stream) {
+    const int nsl = X + Y + Z;
+    const unsigned long long nvox = (unsigned long long)X * Y * Z;
+    MSL_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)nvol * nsl * 4 * sizeof(long long), stream));
+    const size_t smem = (size_t)nsl * 4 * sizeof(int);
+    ProfScope prof(K_SLICE_COUNTS, stream);
+    MSL_CUDA_CHECK(cudaFuncSetAttribute(slice_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned per_cta = 16u * kSliceVecs * kCntThreads;
+    dim3 grid((unsigned)((nvox + per_cta - 1) / per_cta), nvol);
+    slice_counts_kernel<<<grid, kCntThreads, smem, stream>>>(gt, pred, (unsigned)nvox, X, Y, Z, counts);
+    MSL_LAUNCH_CHECK("slice_counts_kernel");
+    const size_t n = (size_t)nvol * nsl;
+    slice_counts_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(counts, nvol, X, Y, Z);
+    MSL_LAUNCH_CHECK("slice_counts_finalize_kernel");
     return MSL_OK;
 }
 

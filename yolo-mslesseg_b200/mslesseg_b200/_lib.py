@@ -41,9 +41,11 @@ _SIGNATURES = {
     "msl_enhance_slices": (C.c_int, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _sz, _i, _vp, _vp]),
     "msl_enhance_images": (C.c_int, [_vp, _i, _i, _i, _i, _sz, _i, _vp, _sz, _i, _vp, _vp]),
     "msl_enhance_volumes": (C.c_int, [_vp, _i, _i, _i, _i, C.POINTER(C.c_void_p), _vp, _vp, _sz, _vp]),
+    "msl_combine_predictions": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "msl_recon": (C.c_int, [_vp, _sz, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "msl_consensus_eval": (C.c_int, [_vp, _vp, _vp, _vp, _i, _sz, _i, _vp, _vp, _vp]),
     "msl_confusion_counts": (C.c_int, [_vp, _vp, _i, _sz, _vp, _vp]),
+    "msl_slice_counts": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "msl_kernel_kinds": (C.c_int, []),
     "msl_kernel_name": (C.c_char_p, [_i]),
     "msl_kernel_launches": (C.c_ulonglong, [C.POINTER(C.c_ulonglong)]),

@@ -49,6 +49,26 @@ def metricas_desde_conteos(tp: int, fp: int, fn: int, tn: int) -> dict:
     }
 
 
+def dsc_desde_conteos(tp: int, fp: int, fn: int) -> float:
+    """DSC (utils/utils.py:455-460) of two binary arrays from their counts, rounded to 3 decimals like the reference."""
+    tp, fp, fn = int(tp), int(fp), int(fn)
+    return float(np.round((2.0 * np.float64(tp)) / (np.float64(tp + fn) + np.float64(tp + fp) + 1e-8), 3))
+
+
+def seleccionar_mejor_corte(conteos_plano, cortes=None):
+    """The selection loop of extras/visualizar_prediccion_corte.py:150-182 on per-slice counts [n_plane, 4] of one
+    patient and plane: DSC of every listed slice (default: all), the first strictly larger value wins.
+    Returns (corte, dsc); (None, -1.0) for an empty list."""
+    conteos = np.asarray(conteos_plano)
+    mejor_corte, mejor_dsc = None, -1.0
+    for corte in (range(conteos.shape[0]) if cortes is None else cortes):
+        tp, fp, fn = (int(v) for v in conteos[int(corte), :3])
+        dsc = dsc_desde_conteos(tp, fp, fn)
+        if dsc > mejor_dsc:
+            mejor_dsc, mejor_corte = dsc, int(corte)
+    return mejor_corte, mejor_dsc
+
+
 def calcular_promedio(metricas_dic: dict) -> dict:
     """scripts/eval.py:144-160: mean and population std of the patients' (already rounded) metrics."""
     if not metricas_dic:

@@ -204,6 +204,42 @@ def enhance_volumes(vol: torch.Tensor, mejoras: Iterable[str] = MEJORAS, planos:
     return result
 
 
+# ------------------------------------------------------------------------------------ R0
+def combine_predictions(masks: Optional[torch.Tensor], inst_offset, rows: int, cols: int, layout: str = "G",
+                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """YOLO instance masks -> one predicted mask per slice (reference scripts/generar_predicciones.py:123-140).
+    masks: float32 [n_inst, mh, mw] (`masks.data` of all slices, concatenated; may be empty), inst_offset: [n + 1]
+    prefix offsets.  layout "G": uint8 [n, rows, cols] {0, 255} (normalizar_prediccion, the input of `recon`);
+    layout "P": uint8 [n, cols, rows] {0, 1} (combinar_predicciones on the PNG-oriented image)."""
+    if layout not in ("G", "P"):
+        raise ValueError("layout must be 'G' or 'P'")
+    if masks is None or masks.numel() == 0:
+        dev = out.device if out is not None else torch.device("cuda", torch.cuda.current_device())
+        masks_ptr, mh, mw = None, 1, 1
+    else:
+        _need_cuda(masks, "masks")
+        if masks.dtype != torch.float32 or masks.dim() != 3:
+            raise ValueError("masks must be float32 [n_inst, mh, mw]")
+        dev, masks_ptr, mh, mw = masks.device, _ptr(masks), int(masks.shape[1]), int(masks.shape[2])
+    off = _index_tensor(inst_offset, dev)
+    n = int(off.numel()) - 1
+    if n < 0:
+        raise ValueError("inst_offset needs n + 1 entries")
+    n_inst = 0 if masks is None else int(masks.shape[0])
+    host_off = off.cpu().tolist()
+    if host_off[0] != 0 or host_off[-1] != n_inst or any(b < a for a, b in zip(host_off, host_off[1:])):
+        raise ValueError("inst_offset must be a non-decreasing prefix table from 0 to the number of instance masks")
+    shape = (n, rows, cols) if layout == "G" else (n, cols, rows)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.uint8, device=dev)
+    _need_cuda(out, "out")
+    if tuple(out.shape) != shape or out.dtype != torch.uint8:
+        raise ValueError(f"out must be uint8 {shape}")
+    L.check(L.load().msl_combine_predictions(masks_ptr, _ptr(off), n, mh, mw, int(rows), int(cols),
+                                             L.OUT_G if layout == "G" else L.OUT_P, _ptr(out), _stream()))
+    return out
+
+
 # ------------------------------------------------------------------------------------ R1-R2
 def recon(slices: torch.Tensor, vol_of_slice, idx_of_slice, plano: str, nvol: int, shape_xyz: Sequence[int],
           dtype: torch.dtype = torch.uint8, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -266,3 +302,17 @@ def confusion_counts(gt: torch.Tensor, pred: torch.Tensor) -> torch.Tensor:
     counts = torch.empty((nvol, 4), dtype=torch.int64, device=gt.device)
     L.check(L.load().msl_confusion_counts(_ptr(gt), _ptr(pred), nvol, nvox, _ptr(counts), _stream()))
     return counts
+
+
+def slice_counts(gt: torch.Tensor, pred: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """Per-slice (tp, fp, fn, tn) of every slice of the three planes in one pass (the counts behind
+    extras/visualizar_prediccion_corte.py seleccionar_mejor_corte).  gt, pred: uint8 [nvol, Z, Y, X].
+    Returns {plano: int64 [nvol, n_plane, 4]}."""
+    _need_cuda(gt, "gt")
+    _need_cuda(pred, "pred")
+    if gt.dtype != torch.uint8 or pred.dtype != torch.uint8 or gt.shape != pred.shape or gt.dim() != 4:
+        raise ValueError("gt and pred must be uint8 tensors [nvol, Z, Y, X] of one shape")
+    nvol, Z, Y, X = (int(d) for d in gt.shape)
+    counts = torch.empty((nvol, Z + Y + X, 4), dtype=torch.int64, device=gt.device)
+    L.check(L.load().msl_slice_counts(_ptr(gt), _ptr(pred), nvol, X, Y, Z, _ptr(counts), _stream()))
+    return {"axial": counts[:, :Z], "coronal": counts[:, Z:Z + Y], "sagital": counts[:, Z + Y:]}
