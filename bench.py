@@ -56,7 +56,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="run the output side on the same stream as the input side")
+    ap.add_argument("--overlap", action="store_true", help="run the output side (recon -> consensus -> eval) on a second stream; measured slower than one stream since the kernels got faster: 3.24 vs 3.19 ms per step")
+    ap.add_argument("--no-overlap", action="store_true", help="(default; kept for older command lines) one stream")
     return ap.parse_args()
 
 
@@ -221,10 +222,10 @@ def run_ours(args):
             dist.all_reduce(table)            # NCCL SUM of the int64 count table
 
     def step():
-        # The two halves of the path are independent (different inputs, different outputs): the output side
-        # (DRAM-bound) runs on a second stream next to the input side (shared-memory / issue bound).
+        # The two halves of the path are independent (different inputs, different outputs); --overlap runs the output
+        # side on a second stream.  One stream is the default: it measured faster once the kernels were tuned.
         cur = torch.cuda.current_stream()
-        if args.no_overlap:
+        if not args.overlap:
             output_side()
         else:
             side.wait_stream(cur)
@@ -232,7 +233,7 @@ def run_ours(args):
                 output_side()
         state["flags"] = ops.lesion_slices(gt)
         ops.enhance_volumes(flair, MEJORAS, PLANOS, outs=outs, workspace=ws)
-        if not args.no_overlap:
+        if args.overlap:
             cur.wait_stream(side)
 
     def barrier():
@@ -369,7 +370,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32+u8 (int64 counts)", "data": "synthetic", "config": workload_config(args, {"volume_chunk": chunk, "chunks": nchunks, "streams": 1 if args.no_overlap else 2}),
+            "dtype": "f32+u8 (int64 counts)", "data": "synthetic", "config": workload_config(args, {"volume_chunk": chunk, "chunks": nchunks, "streams": 2 if args.overlap else 1}),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "stages": stages, "kernels": kernels, "verified": verified,
         }

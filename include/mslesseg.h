@@ -138,6 +138,11 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z,
                         uint8_t* const* outs, const uint8_t* tables,
                         void* ws, size_t ws_bytes, msl_stream_t stream);
 
+/* ---- E7 helper: verificar_grises (utils/utils.py:421-427) on 3-channel images ------------------
+ * cv2.cvtColor(BGR2GRAY) in OpenCV's 8-bit fixed point: (3735 B + 19235 G + 9798 R + 2^14) >> 15.
+ * bgr: uint8 [npx][3] interleaved, gray: uint8 [npx]. */
+int msl_bgr_to_gray(const uint8_t* bgr, size_t npx, uint8_t* gray, msl_stream_t stream);
+
 /* ---- R0: YOLO instance masks -> predicted slice masks (the producer of msl_recon's input) -------
  * Replaces combinar_predicciones (scripts/generar_predicciones.py:123-133: every instance mask > 0.5,
  * cv2.resize INTER_NEAREST to the image shape, maximum over the instances) and normalizar_prediccion

@@ -8,11 +8,8 @@ from mslesseg_b200.compat import reconstruir_volumen as RV
 from mslesseg_b200.compat.Paciente import Paciente
 
 
-def test_verificar_grises_matches_cv2():
-    cv2 = pytest.importorskip("cv2")
+def test_gray_inputs_pass_through_on_the_host():
     rng = np.random.default_rng(1)
-    img = rng.integers(0, 256, (40, 50, 3), dtype=np.uint8)
-    assert np.array_equal(U.verificar_grises(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
     g = rng.integers(0, 256, (8, 9), dtype=np.uint8)
     assert U.verificar_grises(g) is g
     assert np.array_equal(U.normalizar_a_uint8(g), g)          # uint8 passes through without touching the GPU

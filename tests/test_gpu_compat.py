@@ -156,3 +156,13 @@ def test_generar_predicciones_shim(C):
     assert np.array_equal(comb, O.combinar_predicciones(list(masks), (218, 182)))
     assert np.array_equal(GP.normalizar_prediccion(comb), O.normalizar_prediccion(comb))
     assert int(GP.combinar_predicciones([], (218, 182)).sum()) == 0
+
+
+@pytest.mark.gpu
+def test_verificar_grises_matches_cv2(C):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, (40, 50, 3), dtype=np.uint8)
+    assert np.array_equal(C.utils.verificar_grises(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+    img[..., 1] = 255; img[..., 0] = 255; img[..., 2] = 255
+    assert int(C.utils.verificar_grises(img).min()) == 255

@@ -252,6 +252,12 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z, uint8_t
     return MSL_OK;
 }
 
+int msl_bgr_to_gray(const uint8_t* bgr, size_t npx, uint8_t* gray, msl_stream_t stream) {
+    if (npx == 0) return MSL_OK;
+    MSL_REQUIRE(bgr && gray, "NULL pointer");
+    return launch_bgr_to_gray(bgr, npx, gray, (cudaStream_t)stream);
+}
+
 int msl_combine_predictions(const float* masks, const int32_t* inst_offset, int nslices, int mh, int mw,
                             int rows, int cols, int layout, uint8_t* out, msl_stream_t stream) {
     MSL_REQUIRE(nslices >= 0 && rows > 0 && cols > 0, "non-positive size");

@@ -388,6 +388,22 @@ size_t enhance_slices_smem_bytes(int mejora, int npx) {
     return (size_t)kOffHist + hist + (((size_t)npx + 15) & ~(size_t)15);
 }
 
+// cv2.COLOR_BGR2GRAY, 8-bit path: descale(B * 3735 + G * 19235 + R * 9798, 15) (OpenCV color_yuv / color_rgb fixed point)
+__global__ void bgr_to_gray_kernel(const uint8_t* __restrict__ bgr, size_t npx, uint8_t* __restrict__ gray) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned b = bgr[3 * i], g = bgr[3 * i + 1], r = bgr[3 * i + 2];
+        gray[i] = (uint8_t)((b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15);
+    }
+}
+
+int launch_bgr_to_gray(const uint8_t* bgr, size_t npx, uint8_t* gray, cudaStream_t stream) {
+    ProfScope prof(K_BGR2GRAY, stream);
+    const unsigned blocks = (unsigned)((npx + 255) / 256 < 148 * 8 ? (npx + 255) / 256 : 148 * 8);
+    bgr_to_gray_kernel<<<blocks, 256, 0, stream>>>(bgr, npx, gray);
+    MSL_LAUNCH_CHECK("bgr_to_gray_kernel");
+    return MSL_OK;
+}
+
 int launch_enhance_slices(EnhParams p, int dtype, int nslices, cudaStream_t stream) {
     const int npx = p.rows * p.cols;
     p.hist_bytes = p.mejora == MSL_MEJORA_CLAHE ? kHistBytesCLAHE : kHistBytesHE;

@@ -34,9 +34,14 @@ def combinar_predicciones(predicciones, shape):
 
 
 def normalizar_prediccion(pred):
-    """cv2.flip(pred.T, 1) * 255 (pure re-orientation of a tiny array: done on the host like the reference)."""
+    """cv2.flip(pred.T, 1) * 255 for the {0, 1} mask `combinar_predicciones` returns: (height, width) -> (width, height),
+    values {0, 255}.  Runs through the same kernel (identity resize, slice-oriented output)."""
     pred = np.asarray(pred)
-    return np.ascontiguousarray(pred.T[:, ::-1]) * np.uint8(255)
+    if pred.ndim != 2 or pred.max(initial=0) > 1 or pred.min(initial=0) < 0:
+        raise ValueError("normalizar_prediccion: se espera la máscara 2D {0, 1} de combinar_predicciones")
+    height, width = pred.shape
+    masks = torch.from_numpy(np.ascontiguousarray(pred, dtype=np.float32))[None].to(device())
+    return ops.combine_predictions(masks, [0, 1], rows=width, cols=height, layout="G")[0].cpu().numpy()
 
 
 def predicciones_a_cortes(masks, inst_offset, rows, cols):

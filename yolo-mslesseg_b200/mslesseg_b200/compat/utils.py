@@ -129,8 +129,9 @@ def verificar_grises(imagen):
     identity for 2-D images.  The enhancement shims already return images whose gray value is the reference's."""
     imagen = np.asarray(imagen)
     if imagen.ndim == 3 and imagen.shape[2] == 3:
-        b, g, r = (imagen[:, :, i].astype(np.int32) for i in range(3))
-        return ((r * 9798 + g * 19235 + b * 3735 + 16384) >> 15).astype(np.uint8)
+        if imagen.dtype != np.uint8:
+            raise ValueError("verificar_grises: se espera una imagen uint8")
+        return ops.bgr_to_gray(torch.from_numpy(np.ascontiguousarray(imagen)).to(device())).cpu().numpy()
     return imagen
 
 

@@ -316,3 +316,14 @@ def slice_counts(gt: torch.Tensor, pred: torch.Tensor) -> Dict[str, torch.Tensor
     counts = torch.empty((nvol, Z + Y + X, 4), dtype=torch.int64, device=gt.device)
     L.check(L.load().msl_slice_counts(_ptr(gt), _ptr(pred), nvol, X, Y, Z, _ptr(counts), _stream()))
     return {"axial": counts[:, :Z], "coronal": counts[:, Z:Z + Y], "sagital": counts[:, Z + Y:]}
+
+
+def bgr_to_gray(bgr: torch.Tensor) -> torch.Tensor:
+    """cv2.cvtColor(BGR2GRAY) of uint8 [..., 3] images (reference utils/utils.py:421-427 verificar_grises)."""
+    _need_cuda(bgr, "bgr")
+    if bgr.dtype != torch.uint8 or bgr.dim() < 1 or bgr.shape[-1] != 3:
+        raise ValueError("bgr must be uint8 [..., 3]")
+    bgr = bgr.contiguous()
+    gray = torch.empty(bgr.shape[:-1], dtype=torch.uint8, device=bgr.device)
+    L.check(L.load().msl_bgr_to_gray(_ptr(bgr), gray.numel(), _ptr(gray), _stream()))
+    return gray
