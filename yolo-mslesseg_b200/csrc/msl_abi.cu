@@ -215,6 +215,9 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z, uint8_t
         }
         rc = launch_norm_scatter(cvol, nv, X, Y, Z, cstats, so, stream);
         if (rc) return rc;
+        DensePlane dplanes[3];
+        int ndense = 0;
+        bool dense_cl = false;
         for (int pl = 0; pl < 3; ++pl) {
             if (!so.u[pl]) continue;
             uint8_t* dst[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -230,9 +233,18 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z, uint8_t
             clahe_geometry(rows, cols, p);
             const bool dense_ok = dense_supported(rows, cols, dst[MSL_MEJORA_CLAHE] != nullptr) && (align & 3) == 0;
             if (dense_ok) {
-                rc = launch_enhance_dense(U[pl], upitch[pl], nv * n_p[pl], rows, cols, dst[MSL_MEJORA_HE], dst[MSL_MEJORA_CLAHE],
-                                          dst[MSL_MEJORA_GC], dst[MSL_MEJORA_LT], tables, p.cl_th, p.cl_tw, p.cl_clip, p.cl_lut_scale, stream);
-                if (rc) return rc;
+                // the planes of the chunk share one launch (one grid tail instead of three) when they agree on CLAHE
+                const bool cl = dst[MSL_MEJORA_CLAHE] != nullptr;
+                if (ndense > 0 && cl != dense_cl) {
+                    rc = launch_enhance_dense_multi(dplanes, ndense, tables, stream);
+                    if (rc) return rc;
+                    ndense = 0;
+                }
+                dense_cl = cl;
+                DensePlane& q = dplanes[ndense++];
+                q.U = U[pl]; q.u_pitch = upitch[pl]; q.nslices = nv * n_p[pl]; q.rows = rows; q.cols = cols;
+                q.out_he = dst[MSL_MEJORA_HE]; q.out_clahe = dst[MSL_MEJORA_CLAHE]; q.out_gc = dst[MSL_MEJORA_GC]; q.out_lt = dst[MSL_MEJORA_LT];
+                q.th = p.cl_th; q.tw = p.cl_tw; q.clip = p.cl_clip; q.lut_scale = p.cl_lut_scale;
                 continue;
             }
             // generic slice kernel on the staged stack (PNG orientation: G[a, b] = P[cols-1-b, a])
@@ -247,6 +259,10 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z, uint8_t
                 rc = launch_enhance_slices(p, MSL_U8, nv * n_p[pl], stream);
                 if (rc) return rc;
             }
+        }
+        if (ndense > 0) {
+            rc = launch_enhance_dense_multi(dplanes, ndense, tables, stream);
+            if (rc) return rc;
         }
     }
     return MSL_OK;

@@ -23,6 +23,7 @@
 //  * A slice that normalised to all zeros (outside the brain) skips every phase: outputs are table[0] constants.
 #include "msl_common.cuh"
 #include "msl_kernels.h"
+#include <cstring>
 
 namespace msl {
 
@@ -94,9 +95,18 @@ __device__ __forceinline__ void add2(float& o0, float& o1, float a0, float a1, f
     asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(r));
 }
 
+// Up to three stacks (the three planes of a chunk of volumes) in one launch: one grid instead of three means one tail
+// instead of three.  CTA b works on slice b - first[k] of stack k.
+struct DenseLaunch {
+    DenseParams plane[3];
+    int first[4];
+};
+
 template <bool DO_CLAHE>
-__global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseParams p) {
+__global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const __grid_constant__ DenseLaunch L) {
     extern __shared__ __align__(16) uint8_t smem[];
+    const int plane_k = (int)blockIdx.x >= L.first[2] ? 2 : ((int)blockIdx.x >= L.first[1] ? 1 : 0);
+    const DenseParams& p = L.plane[plane_k];
     uint8_t* lutl = smem + kOffLutL;
     uint8_t* lutout = smem + kOffLutOut;
     uint16_t* ustart = reinterpret_cast<uint16_t*>(smem + kOffUstart);
@@ -116,7 +126,7 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const DenseP
     uint8_t* su = R + (DO_CLAHE ? kRBytes : 0);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t s = blockIdx.x;
+    const size_t s = (size_t)((int)blockIdx.x - L.first[plane_k]);
     const uint8_t* in = p.U + s * p.u_pitch;
     const bool want_he = p.out_he != nullptr, want_lut = want_he || p.out_gc || p.out_lt;
 
@@ -589,33 +599,58 @@ bool dense_supported(int rows, int cols, bool clahe) {
            dense_smem_bytes(rows, cols, clahe) <= 227 * 1024;
 }
 
-int launch_enhance_dense(const uint8_t* U, size_t u_pitch, int nslices, int rows, int cols,
-                         uint8_t* out_he, uint8_t* out_clahe, uint8_t* out_gc, uint8_t* out_lt, const uint8_t* tables,
-                         int th, int tw, int clip, float lut_scale, cudaStream_t stream) {
-    if (nslices <= 0 || (!out_he && !out_clahe && !out_gc && !out_lt)) return MSL_OK;
-    const int npx = rows * cols;
-    DenseParams p;
-    p.U = U; p.u_pitch = u_pitch; p.out_he = out_he; p.out_clahe = out_clahe; p.out_gc = out_gc; p.out_lt = out_lt; p.out_pitch = (size_t)npx; p.tables = tables;
-    p.rows = rows; p.cols = cols; p.th = th; p.tw = tw; p.clip = clip; p.lut_scale = lut_scale;
-    p.magic_w = (unsigned)(0x100000000ull / (unsigned)rows) + 1u;
-    const bool cl = out_clahe != nullptr;
-    const size_t smem = dense_smem_bytes(rows, cols, cl);
-    if (!dense_supported(rows, cols, cl) || (u_pitch & 15) || (reinterpret_cast<uintptr_t>(U) & 15) ||
-        ((reinterpret_cast<uintptr_t>(out_he) | reinterpret_cast<uintptr_t>(out_clahe) | reinterpret_cast<uintptr_t>(out_gc) |
-          reinterpret_cast<uintptr_t>(out_lt)) & 3)) {
-        set_error("enhance_dense: unsupported geometry / alignment (%d x %d, %zu B smem)", rows, cols, smem);
-        return MSL_ERR_UNSUPPORTED;
+int launch_enhance_dense_multi(const DensePlane* planes, int nplanes, const uint8_t* tables, cudaStream_t stream) {
+    DenseLaunch L;
+    memset(&L, 0, sizeof(L));
+    int n = 0, total = 0;
+    bool cl = false;
+    size_t smem = 0;
+    for (int i = 0; i < nplanes; ++i) {
+        const DensePlane& q = planes[i];
+        if (q.nslices <= 0 || (!q.out_he && !q.out_clahe && !q.out_gc && !q.out_lt)) continue;
+        if (n == 3) { set_error("enhance_dense: at most three stacks per launch"); return MSL_ERR_ARG; }
+        const bool qcl = q.out_clahe != nullptr;
+        if (n > 0 && qcl != cl) { set_error("enhance_dense: the stacks of one launch must agree on CLAHE"); return MSL_ERR_ARG; }
+        cl = qcl;
+        const size_t sm = dense_smem_bytes(q.rows, q.cols, cl);
+        if (!dense_supported(q.rows, q.cols, cl) || (q.u_pitch & 15) || (reinterpret_cast<uintptr_t>(q.U) & 15) ||
+            ((reinterpret_cast<uintptr_t>(q.out_he) | reinterpret_cast<uintptr_t>(q.out_clahe) | reinterpret_cast<uintptr_t>(q.out_gc) |
+              reinterpret_cast<uintptr_t>(q.out_lt)) & 3)) {
+            set_error("enhance_dense: unsupported geometry / alignment (%d x %d, %zu B smem)", q.rows, q.cols, sm);
+            return MSL_ERR_UNSUPPORTED;
+        }
+        smem = sm > smem ? sm : smem;
+        DenseParams& p = L.plane[n];
+        p.U = q.U; p.u_pitch = q.u_pitch; p.out_he = q.out_he; p.out_clahe = q.out_clahe; p.out_gc = q.out_gc; p.out_lt = q.out_lt;
+        p.out_pitch = (size_t)q.rows * q.cols; p.tables = tables;
+        p.rows = q.rows; p.cols = q.cols; p.th = q.th; p.tw = q.tw; p.clip = q.clip; p.lut_scale = q.lut_scale;
+        p.magic_w = (unsigned)(0x100000000ull / (unsigned)q.rows) + 1u;
+        L.first[n] = total;
+        total += q.nslices;
+        ++n;
     }
+    if (n == 0) return MSL_OK;
+    for (int i = n; i < 4; ++i) L.first[i] = total;        // unused stacks start behind the grid
     ProfScope prof(K_ENH_DENSE, stream);
     if (cl) {
         MSL_CUDA_CHECK(cudaFuncSetAttribute(enhance_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        enhance_dense_kernel<true><<<nslices, kThreads, smem, stream>>>(p);
+        enhance_dense_kernel<true><<<total, kThreads, smem, stream>>>(L);
     } else {
         MSL_CUDA_CHECK(cudaFuncSetAttribute(enhance_dense_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        enhance_dense_kernel<false><<<nslices, kThreads, smem, stream>>>(p);
+        enhance_dense_kernel<false><<<total, kThreads, smem, stream>>>(L);
     }
     MSL_LAUNCH_CHECK("enhance_dense_kernel");
     return MSL_OK;
+}
+
+int launch_enhance_dense(const uint8_t* U, size_t u_pitch, int nslices, int rows, int cols,
+                         uint8_t* out_he, uint8_t* out_clahe, uint8_t* out_gc, uint8_t* out_lt, const uint8_t* tables,
+                         int th, int tw, int clip, float lut_scale, cudaStream_t stream) {
+    DensePlane q;
+    q.U = U; q.u_pitch = u_pitch; q.nslices = nslices; q.rows = rows; q.cols = cols;
+    q.out_he = out_he; q.out_clahe = out_clahe; q.out_gc = out_gc; q.out_lt = out_lt;
+    q.th = th; q.tw = tw; q.clip = clip; q.lut_scale = lut_scale;
+    return launch_enhance_dense_multi(&q, 1, tables, stream);
 }
 
 }  // namespace msl

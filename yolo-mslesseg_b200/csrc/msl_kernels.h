@@ -87,6 +87,13 @@ int launch_norm_scatter(const float* vol, int nvol, int X, int Y, int Z, const u
 size_t dense_u_pitch(int npx);
 size_t dense_smem_bytes(int rows, int cols, bool clahe);
 bool dense_supported(int rows, int cols, bool clahe);
+struct DensePlane {
+    const uint8_t* U; size_t u_pitch; int nslices, rows, cols;
+    uint8_t *out_he, *out_clahe, *out_gc, *out_lt;    // each may be NULL
+    int th, tw, clip; float lut_scale;                // CLAHE geometry of a rows x cols slice
+};
+// up to three stacks in ONE launch (they must agree on whether CLAHE is wanted)
+int launch_enhance_dense_multi(const DensePlane* planes, int nplanes, const uint8_t* tables, cudaStream_t stream);
 int launch_enhance_dense(const uint8_t* U, size_t u_pitch, int nslices, int rows, int cols,
                          uint8_t* out_he, uint8_t* out_clahe, uint8_t* out_gc, uint8_t* out_lt, const uint8_t* tables,
                          int th, int tw, int clip, float lut_scale, cudaStream_t stream);
