@@ -1,15 +1,19 @@
-// Output side of the voxel path: reconstruction (R1-R2), tri-planar vote (R3), confusion counts (R4).
+// Output side of the voxel path: prediction post-processing (R0), reconstruction (R1-R2), tri-planar vote (R3),
+// confusion counts (R4; per volume and per slice).
 //
+//  combine_predictions  YOLO instance masks -> one {0, 255} mask per slice (scripts/generar_predicciones.py:123-140).
 //  recon          predicted 2-D masks (slice orientation, uint8, pixel > 0 == lesion) -> [Z][Y][X] volumes.
 //                 Reference: scripts/reconstruir_volumen.py:146-148 (binarise), :179-186 (insertar_corte),
-//                 :199-213 (zero volume + loop).  Formulated as a GATHER through an inverse slice map so
-//                 every output byte is written exactly once (no memset + scatter): each CTA transposes a
-//                 64x64 byte tile through shared memory, reads run along the slices' fastest axis and
-//                 writes run along x.
+//                 :199-213 (zero volume + loop).  An inverse slice map resolves duplicate indices.  Axial / coronal:
+//                 memset + one CTA per present slice, which assembles the transposed slice in zero-filled shared memory
+//                 from the non-zero bytes only and streams it out with 128-bit stores.  Sagital (the slice index is the
+//                 volume's fastest axis): the kernel writes the whole volume densely, two slice rows per CTA.
+//                 Byte-granular kernels remain as the fallback (float volumes, odd sizes, unaligned buffers).
 //  consensus_eval (ax + co + sa >= umbral) fused with the 4x4 confusion counts of the three planes and the
 //                 consensus against the ground truth.  Reference: scripts/generar_consenso.py:106-109 and
 //                 the boolean sums of utils/utils.py:455-495.  SIMD-within-a-register byte predicates,
 //                 popc, warp shuffles, one int64 atomic per counter per CTA.
+//  slice_counts   the same counts for every slice of the three planes (extras/visualizar_prediccion_corte.py:150-182).
 #include "msl_common.cuh"
 #include "msl_kernels.h"
 
