@@ -316,36 +316,39 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const __grid
     __syncthreads();
 
     // ---------------------------------------------------------------- HE CDF -> LUT; packed HE | GC | LT table
-    if (want_lut) {
+    // Built by warps 0-7 (one gray level per thread).  With CLAHE on, the other warps do not wait for it: they start on
+    // the tile LUTs below, and the table is published by the barrier behind those.
+    auto build_t3 = [&](bool active, auto sync8) {           // active: tid < 256; sync8: a barrier over all callers
         // (with CLAHE on, he_hist[0] is still empty: the background count is npx minus everything else)
         int h = 0, c = 0;
-        if (want_he && tid < 256) {
+        if (want_he && active) {
             h = (int)he_hist[tid];
             c = warp_incl_scan(h, lane);
             if (lane == 31) misc[1 + warp] = c;
             if (h > 0) atomicMin(&misc[0], tid);
         }
-        __syncthreads();
-        if (tid < 256) {
-            uint32_t he = 0;
-            if (want_he) {
-                int total = 0;
+        sync8();
+        if (!active) return;
+        uint32_t he = 0;
+        if (want_he) {
+            int total = 0;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) { const int m = misc[1 + w]; total += m; if (w < warp) c += m; }
-                const int zeros = npx - total;                       // uncounted background pixels (0 without CLAHE)
-                c += zeros;
-                const int i0 = zeros > 0 ? 0 : misc[0];
-                const int h0 = zeros > 0 ? zeros + (int)he_hist[0] : (int)he_hist[i0];
-                if (h0 == npx) he = (uint32_t)i0;
-                else if (tid <= i0) he = 0;
-                else he = sat_u8_rn(__fmul_rn((float)(c - h0), __fdiv_rn(255.0f, (float)(npx - h0))));
-            }
-            // LT: E1 maps the slice maximum to exactly 255 whenever ptp > 0, so the table row is 255; a blank slice is
-            // all zeros and LT_T[255][0] == LT_T[0][0] == 0.
-            const uint32_t gc = __ldg(p.tables + MSL_TAB_GC + tid), lt = __ldg(p.tables + MSL_TAB_LT + 255 * 256 + tid);
-            t3[tid] = he | (gc << 8) | (lt << 16);
+            for (int w = 0; w < 8; ++w) { const int m = misc[1 + w]; total += m; if (w < warp) c += m; }
+            const int zeros = npx - total;                       // uncounted background pixels (0 without CLAHE)
+            c += zeros;
+            const int i0 = zeros > 0 ? 0 : misc[0];
+            const int h0 = zeros > 0 ? zeros + (int)he_hist[0] : (int)he_hist[i0];
+            if (h0 == npx) he = (uint32_t)i0;
+            else if (tid <= i0) he = 0;
+            else he = sat_u8_rn(__fmul_rn((float)(c - h0), __fdiv_rn(255.0f, (float)(npx - h0))));
         }
-        __syncthreads();
+        // LT: E1 maps the slice maximum to exactly 255 whenever ptp > 0, so the table row is 255; a blank slice is
+        // all zeros and LT_T[255][0] == LT_T[0][0] == 0.
+        const uint32_t gc = __ldg(p.tables + MSL_TAB_GC + tid), lt = __ldg(p.tables + MSL_TAB_LT + 255 * 256 + tid);
+        t3[tid] = he | (gc << 8) | (lt << 16);
+    };
+    // one lookup per pixel for HE, GC and LT; the 4 x 3 bytes of a word are transposed into three output words
+    auto map_t3 = [&]() {
         uint32_t* o_he = reinterpret_cast<uint32_t*>(p.out_he ? p.out_he + s * p.out_pitch : nullptr);
         uint32_t* o_gc = reinterpret_cast<uint32_t*>(p.out_gc ? p.out_gc + s * p.out_pitch : nullptr);
         uint32_t* o_lt = reinterpret_cast<uint32_t*>(p.out_lt ? p.out_lt + s * p.out_pitch : nullptr);
@@ -366,14 +369,23 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const __grid
             if (p.out_gc) p.out_gc[s * p.out_pitch + o] = (uint8_t)(a0 >> 8);
             if (p.out_lt) p.out_lt[s * p.out_pitch + o] = (uint8_t)(a0 >> 16);
         }
+    };
+    if (!DO_CLAHE) {
+        if (want_lut) {
+            build_t3(tid < 256, [] { __syncthreads(); });
+            __syncthreads();
+            map_t3();
+        }
+        return;
     }
-    if (!DO_CLAHE) return;
+    if (want_lut && warp < 8) build_t3(true, [] { asm volatile("bar.sync 1, 256;" ::: "memory"); });
 
     // ---------------------------------------------------------------- CLAHE: fold u-bins into L-bins, clip, CDF -> tile LUTs
     // (OpenCV CLAHE_CalcLut_Body).  One warp per tile, 8 L-bins per lane.
     const bool long_fold = misc[21] != 0;
     const int L0 = lutl[0], area = th * tw, clip = p.clip;
-    for (int t = warp; t < 64; t += kWarps) {
+    // tiles 0-47 go to warps 8-23 (three each), tiles 48-63 to warps 0-7 (two each, after the table above)
+    for (int t = warp >= 8 ? warp - 8 : 48 + warp; t < (warp >= 8 ? 48 : 64); t += (warp >= 8 ? 16 : 8)) {
         const unsigned* hu = hist + t * 256;
         int hb[8];
         if (!long_fold) {
@@ -458,6 +470,7 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const __grid
         }
     }
     __syncthreads();
+    if (want_lut) map_t3();                                  // HE | GC | LT outputs (the table was published by the barrier above)
     const bool use_tz = cols <= (kPairStride - kPairTy) / 4;
     // Pair tables: PT[ty][u][j] = (T[ty][tx1][LUT_L[u]], T[ty][tx2][LUT_L[u]]) as one 16-bit entry for the nine
     // horizontal neighbour pairs (tx1, tx2) = (0,0), (0,1), ..., (6,7), (7,7).  One 16-bit read fetches both operands
