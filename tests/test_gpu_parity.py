@@ -128,6 +128,50 @@ def test_noise_volume_golden(ops, torch_mod, golden, cuda_device):
             assert sha(G) == g["planes"][plano][mej], (plano, mej, "volume mode")
 
 
+def _fuzz_volume(seed):
+    """Random shape (even X and Y -> dense kernels; sometimes odd -> fallbacks) and one of several value regimes."""
+    rng = np.random.default_rng(seed)
+    X, Y, Z = (int(2 * rng.integers(8, 40)) for _ in range(3))
+    if seed % 5 == 4:
+        X += 1
+    if seed % 7 == 6:
+        Z += 1
+    regime = seed % 6
+    v = rng.standard_normal((Z, Y, X)).astype(np.float32)
+    if regime == 0:
+        v = np.round(v * 300 + 500).astype(np.float32)                      # integer-valued intensities
+    elif regime == 1:
+        v = (v * np.float32(1.0e-3) + np.float32(5.0)).astype(np.float32)   # tiny range on a large offset
+    elif regime == 2:
+        v = (v * np.float32(3.0e6)).astype(np.float32)                      # large magnitudes, negative values
+    elif regime == 3:
+        v = np.abs(v).astype(np.float32) ** np.float32(4.0)                 # heavy-tailed: most pixels in a few low bins
+    elif regime == 4:
+        v = np.floor(v * 2).astype(np.float32)                              # a handful of distinct levels
+    # skull-stripped look: a centred ellipsoid of signal, exact zeros elsewhere; one constant plane
+    zz, yy, xx = np.ogrid[0:Z, 0:Y, 0:X]
+    inside = ((zz - Z / 2) / (0.42 * Z)) ** 2 + ((yy - Y / 2) / (0.45 * Y)) ** 2 + ((xx - X / 2) / (0.4 * X)) ** 2 <= 1.0
+    if regime != 5:
+        v = np.where(inside, v, np.float32(0.0)).astype(np.float32)
+    v[Z // 2, :, :] = v[Z // 2, 0, 0]
+    return v, (X, Y, Z)
+
+
+@pytest.mark.parametrize("seed", list(range(300, 312)))
+def test_fuzz_volume_mode_vs_oracle(ops, torch_mod, cuda_device, seed):
+    """Random shapes and value regimes, all enhancements and planes, volume mode against the oracle."""
+    torch = torch_mod
+    nv, shape_xyz = _fuzz_volume(seed)
+    vol = torch.from_numpy(nv).to(cuda_device)[None].contiguous()
+    vxyz = S.as_xyz(nv).astype(np.float64)
+    res = ops.enhance_volumes(vol)
+    for plano in PLANOS:
+        for mej in MEJORAS:
+            want = oracle_all(vxyz, plano, mej)
+            G = res[(mej, plano)][0].flip(-2).transpose(-1, -2).contiguous().cpu().numpy()
+            assert np.array_equal(G, want), explain(G, want, f"seed {seed} {shape_xyz} {plano} {mej}")
+
+
 def test_volume_mode_custom_tables(ops, torch_mod, cuda_device):
     """The table block is a parameter: any non-decreasing LUT_L must work (the volume path folds gray histograms into
     L histograms through it).  This one starts above 0, folds up to four grays into one L and leaves gaps."""
