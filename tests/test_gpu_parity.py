@@ -464,6 +464,38 @@ def test_slice_counts_vs_oracle(ops, torch_mod, cuda_device, shape_xyz):
         assert torch.equal(got2[plano], got[plano])
 
 
+@pytest.mark.parametrize("seed", list(range(500, 510)))
+def test_fuzz_output_side_vs_oracle(ops, torch_mod, cuda_device, seed):
+    """Random shapes, mask densities and slice subsets through recon -> consensus -> counts -> per-slice counts."""
+    torch = torch_mod
+    rng = np.random.default_rng(seed)
+    X, Y, Z = (int(rng.integers(6, 70)) for _ in range(3))
+    if seed % 2 == 0:
+        X, Y, Z = 2 * (X // 2 + 1), 2 * (Y // 2 + 1), 2 * (Z // 2 + 1)
+    dens = float(rng.choice([0.002, 0.05, 0.5, 1.0]))
+    gt = (rng.random((Z, Y, X)) < 0.05).astype(np.uint8)
+    vols = {}
+    for plano in PLANOS:
+        n_p, rows, cols = ops.plane_dims(plano, X, Y, Z)
+        idx = sorted(set(int(i) for i in rng.choice(n_p, size=int(rng.integers(1, n_p + 1)), replace=False)))
+        sl = ((rng.random((len(idx), rows, cols)) < dens) * rng.integers(1, 256, size=(len(idx), rows, cols))).astype(np.uint8)
+        want = O.reconstruir(list(sl), idx, (X, Y, Z), plano).transpose(2, 1, 0).astype(np.uint8)
+        got = ops.recon(torch.from_numpy(sl).to(cuda_device), [0] * len(idx), idx, plano, 1, (X, Y, Z))
+        assert np.array_equal(got[0].cpu().numpy(), want), (seed, (X, Y, Z), plano, dens)
+        vols[plano] = got
+    gtd = torch.from_numpy(gt).to(cuda_device)[None]
+    cons, counts = ops.consensus_eval(vols["axial"], vols["coronal"], vols["sagital"], gtd, 2)
+    wc = O.combinar_volumenes(*(vols[p][0].cpu().numpy().astype(np.float64) for p in PLANOS), 2)
+    assert np.array_equal(cons[0].cpu().numpy(), wc)
+    assert counts[0, 3].tolist() == list(O.confusion_counts(gt, wc))
+    sc = ops.slice_counts(gtd, cons)
+    gx, px = gt.transpose(2, 1, 0), wc.transpose(2, 1, 0)
+    for plano in PLANOS:
+        n_p = gx.shape[O.plane_axis(plano)]
+        want = np.array([O.confusion_counts(O.slice_of(gx, plano, i), O.slice_of(px, plano, i)) for i in range(n_p)])
+        assert np.array_equal(sc[plano][0].cpu().numpy(), want), (seed, plano)
+
+
 def test_no_cpu_fallback(ops, torch_mod):
     torch = torch_mod
     with pytest.raises(TypeError):
