@@ -138,6 +138,17 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z,
                         uint8_t* const* outs, const uint8_t* tables,
                         void* ws, size_t ws_bytes, msl_stream_t stream);
 
+/* ---- E8 container: PNG files around the imsave pixels (encode side) ---------------
+ * Replaces the per-slice PNG encode behind plt.imsave (scripts/extraer_dataset.py:192,197).  pixels: uint8
+ * [n][H][W][channels], channels 4 (RGBA, colour type 6 - what imsave writes) or 1 (gray, colour type 0).
+ * out: n complete PNG files of msl_png_bytes(H, W, channels) bytes each, file i at out + i * out_pitch_bytes
+ * (out 16-byte aligned, out_pitch_bytes a multiple of 16 and >= the file size rounded up to 16; the padding is
+ * zeroed).  The IDAT chunk holds a zlib stream of STORED deflate blocks: the files decode to exactly `pixels`,
+ * compression is left to whoever wants it.  Images whose file exceeds ~200 KB are refused (MSL_ERR_UNSUPPORTED). */
+size_t msl_png_bytes(int H, int W, int channels);
+int msl_png_pack(const uint8_t* pixels, int n, int H, int W, int channels,
+                 uint8_t* out, size_t out_pitch_bytes, msl_stream_t stream);
+
 /* ---- E7 helper: verificar_grises (utils/utils.py:421-427) on 3-channel images ------------------
  * cv2.cvtColor(BGR2GRAY) in OpenCV's 8-bit fixed point: (3735 B + 19235 G + 9798 R + 2^14) >> 15.
  * bgr: uint8 [npx][3] interleaved, gray: uint8 [npx]. */

@@ -330,6 +330,37 @@ def num_cortes_percentil(conteos: list, percentil: int = 50) -> int:
 
 
 # --------------------------------------------------------------------------------------
+# E8 container  PNG file around the imsave pixels (encode side)
+# --------------------------------------------------------------------------------------
+
+def png_stored(pixels: np.ndarray) -> bytes:
+    """A complete 8-bit PNG file (colour type 6 for [H, W, 4], 0 for [H, W]) whose IDAT holds a zlib stream of STORED
+    deflate blocks: filter byte 0 per scanline, blocks of at most 65535 bytes, Adler-32 of the raw scanlines, CRC-32 per
+    chunk (PNG 1.2 / RFC 1950 / RFC 1951).  Decodes to exactly `pixels` - the image scripts/extraer_dataset.py:192,197
+    writes through plt.imsave - while leaving the compression to whoever wants it."""
+    import struct
+    import zlib
+    a = np.ascontiguousarray(pixels, dtype=np.uint8)
+    if a.ndim == 2:
+        a = a[:, :, None]
+    H, W, ch = a.shape
+    assert ch in (1, 4)
+    raw = np.concatenate([np.zeros((H, 1), np.uint8), a.reshape(H, W * ch)], axis=1).tobytes()
+    z = bytearray(b"\x78\x01")
+    nblk = max(1, -(-len(raw) // 65535))
+    for k in range(nblk):
+        blk = raw[k * 65535:(k + 1) * 65535]
+        z += struct.pack("<BHH", 1 if k == nblk - 1 else 0, len(blk), len(blk) ^ 0xFFFF) + blk
+    z += struct.pack(">I", zlib.adler32(raw) & 0xFFFFFFFF)
+
+    def chunk(tag: bytes, data: bytes) -> bytes:
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    ihdr = struct.pack(">IIBBBBB", W, H, 8, 6 if ch == 4 else 0, 0, 0, 0)
+    return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", ihdr) + chunk(b"IDAT", bytes(z)) + chunk(b"IEND", b"")
+
+
+# --------------------------------------------------------------------------------------
 # R0  YOLO instance masks -> one predicted slice mask (the producer of R1's input; SURVEY 8f-3)
 # --------------------------------------------------------------------------------------
 

@@ -56,4 +56,24 @@ for plano in ("axial", "coronal", "sagital"):
 cpu_ms = (time.perf_counter() - t0) * 1e3 * B
 out["slice_counts"] = {"volumes": B, "ms": ms, "algorithmic_bytes": alg, "gb_s": alg / ms / 1e6, "frac_of_peak": alg / ms / 1e6 / peak,
                        "gvoxel_s": gt.numel() / ms / 1e6, "cpu_oracle_ms_same_work": cpu_ms, "cpu_cores": 1}
+# ---- 8f-1 (encode side): PNG files for 1184 RGBA slices of 218 x 182 (eight per SM)
+NPNG = 1184
+rgba = torch.randint(0, 256, (NPNG, 218, 182, 4), dtype=torch.uint8, device=dev)
+ms = timed(lambda: ops.png_pack(rgba))
+files, size = ops.png_pack(rgba)
+alg = rgba.numel() + NPNG * size
+import io
+try:
+    from PIL import Image
+    h0 = rgba[0].cpu().numpy()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        Image.fromarray(h0, mode="RGBA").save(io.BytesIO(), format="PNG")
+    cpu_ms = (time.perf_counter() - t0) / 5 * 1e3 * NPNG
+except ImportError:
+    cpu_ms = None
+out["png_pack"] = {"images": NPNG, "shape": [218, 182, 4], "file_bytes": size, "ms": ms, "algorithmic_bytes": alg,
+                   "gb_s": alg / ms / 1e6, "frac_of_peak": alg / ms / 1e6 / peak,
+                   "cpu_pillow_deflate_ms_same_images": cpu_ms, "cpu_cores": 1,
+                   "note": "pixels read + file written; the CPU figure is Pillow's PNG encoder (deflate) on random pixels"}
 print(json.dumps(out))

@@ -496,6 +496,29 @@ def test_fuzz_output_side_vs_oracle(ops, torch_mod, cuda_device, seed):
         assert np.array_equal(sc[plano][0].cpu().numpy(), want), (seed, plano)
 
 
+@pytest.mark.parametrize("shape", [(3, 218, 182, 4), (2, 182, 182, 4), (2, 5, 7, 4), (1, 1, 1, 4), (2, 33, 21), (1, 218, 182), (1, 163, 100, 4)])
+def test_png_pack_matches_container_oracle(ops, torch_mod, cuda_device, shape):
+    """PNG files with stored deflate blocks: byte-identical to the container oracle (zlib's CRC-32 /
+    Adler-32) and decoded back to the input pixels by Pillow; block boundaries at 65535 bytes included."""
+    import io
+    torch = torch_mod
+    rng = np.random.default_rng(sum(shape))
+    px = rng.integers(0, 256, shape, dtype=np.uint8)
+    files, size = ops.png_pack(torch.from_numpy(px).to(cuda_device))
+    host = files.cpu().numpy()
+    assert int(host[:, size:].sum()) == 0
+    for i in range(shape[0]):
+        got = host[i, :size].tobytes()
+        assert got == O.png_stored(px[i]), (shape, i)
+        try:
+            from PIL import Image
+        except ImportError:
+            continue
+        assert np.array_equal(np.array(Image.open(io.BytesIO(got))), px[i])
+    with pytest.raises(Exception):
+        ops.png_pack(torch.zeros((1, 400, 300, 4), dtype=torch.uint8, device=cuda_device))    # 480 KB: refused, not mangled
+
+
 def test_no_cpu_fallback(ops, torch_mod):
     torch = torch_mod
     with pytest.raises(TypeError):

@@ -220,3 +220,31 @@ def test_resize_nearest_index_matches_cv2():
         want = cv2.resize(a, (dw, dh), interpolation=cv2.INTER_NEAREST)
         got = a[O.resize_nearest_index(dh, sh)][:, O.resize_nearest_index(dw, sw)]
         assert np.array_equal(got, want), (sh, sw, dh, dw)
+
+
+def test_png_container_oracle_decodes():
+    """The stored-deflate PNG container restated in oracle.png_stored is a valid PNG: zlib and Pillow / cv2 read it back."""
+    import io, struct, zlib
+    rng = np.random.default_rng(9)
+    for shape in [(218, 182, 4), (5, 7, 4), (33, 21), (300, 200, 4)]:
+        a = rng.integers(0, 256, shape, dtype=np.uint8)
+        b = O.png_stored(a)
+        assert b[:8] == b"\x89PNG\r\n\x1a\n"
+        # walk the chunks, check every CRC, inflate the IDAT
+        off, idat = 8, b""
+        while off < len(b):
+            n, tag = struct.unpack(">I4s", b[off:off + 8])
+            data = b[off + 8:off + 8 + n]
+            assert struct.unpack(">I", b[off + 8 + n:off + 12 + n])[0] == zlib.crc32(tag + data) & 0xFFFFFFFF
+            if tag == b"IDAT":
+                idat += data
+            off += 12 + n
+        H, W = shape[:2]
+        ch = shape[2] if len(shape) == 3 else 1
+        raw = zlib.decompress(idat)
+        assert len(raw) == H * (1 + W * ch)
+        rows = np.frombuffer(raw, np.uint8).reshape(H, 1 + W * ch)
+        assert int(rows[:, 0].sum()) == 0 and np.array_equal(rows[:, 1:].reshape(a.shape), a)
+        cv2 = pytest.importorskip("cv2")
+        d = cv2.imdecode(np.frombuffer(b, np.uint8), cv2.IMREAD_UNCHANGED)
+        assert np.array_equal(d[..., [2, 1, 0, 3]] if a.ndim == 3 else d, a)

@@ -268,6 +268,23 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z, uint8_t
     return MSL_OK;
 }
 
+size_t msl_png_bytes(int H, int W, int channels) {
+    if (H <= 0 || W <= 0 || (channels != 1 && channels != 4)) return 0;
+    return png_file_bytes(H, W, channels);
+}
+
+int msl_png_pack(const uint8_t* pixels, int n, int H, int W, int channels, uint8_t* out, size_t out_pitch_bytes, msl_stream_t stream) {
+    MSL_REQUIRE(n >= 0 && H > 0 && W > 0, "non-positive size");
+    MSL_REQUIRE(channels == 1 || channels == 4, "channels %d no válido (1 o 4)", channels);
+    if (n == 0) return MSL_OK;
+    MSL_REQUIRE(pixels && out, "NULL pointer");
+    MSL_REQUIRE((unsigned long long)H * ((unsigned long long)W * channels + 1) < 0x7fffffffull, "image too large");
+    const size_t need = (png_file_bytes(H, W, channels) + 15) & ~(size_t)15;
+    MSL_REQUIRE((out_pitch_bytes & 15) == 0 && out_pitch_bytes >= need && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "out must be 16-byte aligned with a pitch that is a multiple of 16 and >= %zu", need);
+    return launch_png_pack(pixels, n, H, W, channels, out, out_pitch_bytes, (cudaStream_t)stream);
+}
+
 int msl_bgr_to_gray(const uint8_t* bgr, size_t npx, uint8_t* gray, msl_stream_t stream) {
     if (npx == 0) return MSL_OK;
     MSL_REQUIRE(bgr && gray, "NULL pointer");

@@ -24,7 +24,8 @@ enum KernelKind {
     K_COMBINE_PRED = 20,  // YOLO instance masks -> predicted slice mask
     K_SLICE_COUNTS = 21,  // per-slice confusion counts of the three planes
     K_BGR2GRAY = 22,
-    K_NKIND = 23
+    K_PNG_PACK = 23,
+    K_NKIND = 24
 };
 
 // RAII: counts the launch and, when profiling is enabled, brackets it with CUDA events on `stream`.
@@ -107,6 +108,8 @@ int launch_recon(const uint8_t* slices, size_t slice_pitch, const int32_t* vol_o
 int launch_combine_predictions(const float* masks, const int32_t* inst_offset, int nslices, int mh, int mw, int rows, int cols,
                                int layout, uint8_t* out, cudaStream_t stream);
 int launch_bgr_to_gray(const uint8_t* bgr, size_t npx, uint8_t* gray, cudaStream_t stream);
+size_t png_file_bytes(int H, int W, int ch);
+int launch_png_pack(const uint8_t* pixels, int n, int H, int W, int ch, uint8_t* out, size_t out_pitch, cudaStream_t stream);
 int launch_slice_counts(const uint8_t* gt, const uint8_t* pred, int nvol, int X, int Y, int Z, long long* counts, cudaStream_t stream);
 int launch_consensus_eval(const uint8_t* ax, const uint8_t* co, const uint8_t* sa, const uint8_t* gt,
                           int nvol, size_t nvox, int umbral, uint8_t* consenso, long long* counts, cudaStream_t stream);

@@ -41,6 +41,8 @@ _SIGNATURES = {
     "msl_enhance_slices": (C.c_int, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _sz, _i, _vp, _vp]),
     "msl_enhance_images": (C.c_int, [_vp, _i, _i, _i, _i, _sz, _i, _vp, _sz, _i, _vp, _vp]),
     "msl_enhance_volumes": (C.c_int, [_vp, _i, _i, _i, _i, C.POINTER(C.c_void_p), _vp, _vp, _sz, _vp]),
+    "msl_png_bytes": (_sz, [_i, _i, _i]),
+    "msl_png_pack": (C.c_int, [_vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "msl_bgr_to_gray": (C.c_int, [_vp, _sz, _vp, _vp]),
     "msl_combine_predictions": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "msl_recon": (C.c_int, [_vp, _sz, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

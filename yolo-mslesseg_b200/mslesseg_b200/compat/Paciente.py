@@ -144,15 +144,15 @@ class Paciente:
         return _M.ventana_central(self.indices_cortes_con_lesion(), num_cortes)
 
     # ---- batched extraction (utils/Paciente.py:281-308) ----
-    def cortes_con_lesion_gris(self, num_cortes=None, layout="G"):
+    def cortes_con_lesion_gris(self, num_cortes=None, layout="G", en_dispositivo=False):
         """{modality: (indices, uint8 stack)}: verificar_grises(aplicar_mejora(slice)) for the selected slices in ONE
         kernel launch per modality - what guardar_cortes consumes.  layout "G" (slice orientation), "P" (PNG
-        orientation) or "PNG_RGBA" (the pixels plt.imsave would write)."""
+        orientation) or "PNG_RGBA" (the pixels plt.imsave would write).  en_dispositivo: keep the stack on the GPU."""
         indices = self.indices_a_usar(num_cortes)
         res = {}
         for m in self.modalidad:
             st = ops.enhance_slices(self._vol_dev(m), self.mejora, self.plano, [0] * len(indices), indices, layout=layout)
-            res[m] = (indices, st.cpu().numpy())
+            res[m] = (indices, st if en_dispositivo else st.cpu().numpy())
         return res
 
     def cortes_con_lesion_img(self, num_cortes=None):

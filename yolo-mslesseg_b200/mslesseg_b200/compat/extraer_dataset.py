@@ -5,7 +5,6 @@ from pathlib import Path
 
 import numpy as np
 import torch
-from PIL import Image
 
 from .. import metrics as _M
 from .. import ops
@@ -32,17 +31,25 @@ def resolver_num_cortes(num_cortes, input_dir, plano, modalidad):
     raise ValueError(f"Formato de num_cortes no válido: {num_cortes}.")
 
 
+def _escribir_pngs(rgba_dev, rutas):
+    """One PNG file per image of the device stack [n, H, W, 4]: the files are assembled on the GPU (ops.png_pack: stored
+    deflate blocks, CRC-32 / Adler-32 computed in the kernel), the host only writes the bytes."""
+    files, size = ops.png_pack(rgba_dev)
+    host = files.cpu().numpy()
+    for n, ruta in enumerate(rutas):
+        with open(ruta, "wb") as f:
+            f.write(host[n, :size].tobytes())
+
+
 def guardar_cortes(paciente, images_dir, gt_masks_dir, num_cortes):
     """Writes the image and mask PNGs of guardar_cortes (:174-197).  The RGBA pixels are what
     plt.imsave(path, corte.T, cmap="gray", origin="lower") produces (orientation, second normalisation and gray
-    colormap computed on the GPU, layout PNG_RGBA); Pillow only encodes them."""
+    colormap computed on the GPU, layout PNG_RGBA), and so are the PNG files themselves."""
     images_dir, gt_masks_dir = Path(images_dir), Path(gt_masks_dir)
     indices = paciente.indices_a_usar(num_cortes)
     if not indices:
         raise ValueError(f"No se encontraron cortes válidos para el paciente {paciente.id}.")
-    for modalidad, (idx, rgba) in paciente.cortes_con_lesion_gris(num_cortes, layout="PNG_RGBA").items():
-        for n, i in enumerate(idx):
-            Image.fromarray(rgba[n], mode="RGBA").save(images_dir / f"{paciente.id}_{modalidad}_{i}.png")
-    masks = ops.enhance_slices(paciente._gt_dev(), None, paciente.plano, [0] * len(indices), indices, layout="PNG_RGBA").cpu().numpy()
-    for n, i in enumerate(indices):
-        Image.fromarray(masks[n], mode="RGBA").save(gt_masks_dir / f"{paciente.id}_{i}.png")
+    for modalidad, (idx, rgba) in paciente.cortes_con_lesion_gris(num_cortes, layout="PNG_RGBA", en_dispositivo=True).items():
+        _escribir_pngs(rgba, [images_dir / f"{paciente.id}_{modalidad}_{i}.png" for i in idx])
+    masks = ops.enhance_slices(paciente._gt_dev(), None, paciente.plano, [0] * len(indices), indices, layout="PNG_RGBA")
+    _escribir_pngs(masks, [gt_masks_dir / f"{paciente.id}_{i}.png" for i in indices])

@@ -327,3 +327,20 @@ def bgr_to_gray(bgr: torch.Tensor) -> torch.Tensor:
     gray = torch.empty(bgr.shape[:-1], dtype=torch.uint8, device=bgr.device)
     L.check(L.load().msl_bgr_to_gray(_ptr(bgr), gray.numel(), _ptr(gray), _stream()))
     return gray
+
+
+def png_pack(pixels: torch.Tensor):
+    """Complete PNG files for a batch of images: uint8 [n, H, W, 4] (RGBA, what plt.imsave writes; reference
+    scripts/extraer_dataset.py:192,197) or [n, H, W] (gray).  Returns (files, size): uint8 [n, pitch] on the device and
+    the length of each file; `files[i, :size].cpu().numpy().tobytes()` is file i (stored deflate blocks)."""
+    _need_cuda(pixels, "pixels")
+    if pixels.dtype != torch.uint8 or pixels.dim() not in (3, 4) or (pixels.dim() == 4 and pixels.shape[-1] != 4):
+        raise ValueError("pixels must be uint8 [n, H, W, 4] or [n, H, W]")
+    pixels = pixels.contiguous()
+    n, H, W = (int(d) for d in pixels.shape[:3])
+    ch = 4 if pixels.dim() == 4 else 1
+    size = int(L.load().msl_png_bytes(H, W, ch))
+    pitch = (size + 15) & ~15
+    out = torch.empty((n, pitch), dtype=torch.uint8, device=pixels.device)
+    L.check(L.load().msl_png_pack(_ptr(pixels), n, H, W, ch, _ptr(out), pitch, _stream()))
+    return out, size
