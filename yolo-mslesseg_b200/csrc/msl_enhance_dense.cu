@@ -29,7 +29,7 @@ namespace msl {
 
 namespace {
 
-constexpr int kThreads = 768;
+constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 
 struct DenseParams {
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const __grid
 
     // ---------------------------------------------------------------- load
     // The slice's 128-bit loads are issued first; the table copies and the histogram clear overlap their latency.
-    constexpr int kMaxVec = 4;                                   // 4 x 16 B per thread in flight (covers 48 KB slices)
+    constexpr int kMaxVec = 5;                                   // 5 x 16 B per thread in flight (covers 40 KB slices)
     const int nvec = npx >> 4;
     const uint4* in4 = reinterpret_cast<const uint4*>(in);
     uint4 pre[kMaxVec];
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const __grid
         __syncthreads();
         // HE's histogram = sum of the 64 tile histograms (before the CLAHE padding is added)
         if (want_he) {
-            // thread = one gray level and a third of the tiles (768 threads = 3 x 256); partial sums meet in he_hist
+            // thread = one gray level and 1 / kParts of the tiles; partial sums meet in he_hist
             constexpr int kParts = kThreads / 256;
             const int part = tid >> 8, u = tid & 255;
             unsigned acc = 0;
@@ -384,8 +384,9 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const __grid
     // (OpenCV CLAHE_CalcLut_Body).  One warp per tile, 8 L-bins per lane.
     const bool long_fold = misc[21] != 0;
     const int L0 = lutl[0], area = th * tw, clip = p.clip;
-    // tiles 0-47 go to warps 8-23 (three each), tiles 48-63 to warps 0-7 (two each, after the table above)
-    for (int t = warp >= 8 ? warp - 8 : 48 + warp; t < (warp >= 8 ? 48 : 64); t += (warp >= 8 ? 16 : 8)) {
+    // warps 0-7 come from the table above and take the last kLowTiles tiles, the other warps share the rest
+    constexpr int kLowTiles = kWarps >= 24 ? 16 : 24, kHighTiles = 64 - kLowTiles;
+    for (int t = warp >= 8 ? warp - 8 : kHighTiles + warp; t < (warp >= 8 ? kHighTiles : 64); t += (warp >= 8 ? kWarps - 8 : 8)) {
         const unsigned* hu = hist + t * 256;
         int hb[8];
         if (!long_fold) {
