@@ -516,6 +516,12 @@ __global__ void __launch_bounds__(kCntThreads, 4) consensus_eval_kernel(const Vo
             const uint2 wg = cnt ? __ldg(gt + g) : make_uint2(0, 0);
             const uint2 xg = cnt ? __ldg(gt + gb) : make_uint2(0, 0);
             uint2 r, r2;
+            // masks are ~99 % zeros: sixteen background voxels (all four volumes zero, threshold above zero) only count
+            if (a.umbral > 0 && (wa.x | wa.y | wc.x | wc.y | ws.x | ws.y | wg.x | wg.y | xa.x | xa.y | xc.x | xc.y | xs.x | xs.y | xg.x | xg.y) == 0) {
+                if (out) { out[g] = make_uint2(0, 0); if (has2) out[g2] = make_uint2(0, 0); }
+                acc.n += has2 ? 16 : 8;
+                continue;
+            }
             r.x = vote4(wa.x, wc.x, ws.x, a.umbral);
             r.y = vote4(wa.y, wc.y, ws.y, a.umbral);
             r2.x = vote4(xa.x, xc.x, xs.x, a.umbral);
@@ -568,6 +574,7 @@ __global__ void __launch_bounds__(kCntThreads) confusion_counts_kernel(const uin
         };
         for (size_t g = (size_t)blockIdx.x * kCntThreads + threadIdx.x; g < ng; g += (size_t)gridDim.x * kCntThreads) {
             const uint2 wg = __ldg(g8 + g), wp = __ldg(p8 + g);
+            if ((wg.x | wg.y | wp.x | wp.y) == 0) { acc.n += 8; continue; }       // background: only counted
             word(wg.x, wp.x);
             word(wg.y, wp.y);
             if (++it == kFlush) { acc.flush(); it = 0; }
