@@ -172,6 +172,29 @@ def test_fuzz_volume_mode_vs_oracle(ops, torch_mod, cuda_device, seed):
             assert np.array_equal(G, want), explain(G, want, f"seed {seed} {shape_xyz} {plano} {mej}")
 
 
+def test_volume_mode_mixed_outputs_through_the_abi(ops, torch_mod, cuda_device):
+    """Any subset of the 12 (enhancement, plane) outputs can be requested through the C ABI; planes that disagree on
+    CLAHE cannot share one dense launch and are launched separately."""
+    import ctypes as C
+    from mslesseg_b200 import _lib as L
+    torch = torch_mod
+    nv = _noise(77, (44, 38, 30))
+    vol = torch.from_numpy(nv).to(cuda_device)[None].contiguous()
+    X, Y, Z = 44, 38, 30
+    want = {("CLAHE", "axial"), ("GC", "coronal"), ("HE", "sagital"), ("CLAHE", "sagital"), ("LT", "axial")}
+    ptrs = (C.c_void_p * 12)()
+    outs = {}
+    for mej, pl in want:
+        n_p, rows, cols = ops.plane_dims(pl, X, Y, Z)
+        outs[(mej, pl)] = torch.full((1, n_p, cols, rows), 99, dtype=torch.uint8, device=cuda_device)
+        ptrs[(L.MEJORA_ID[mej] - 1) * 3 + L.PLANO_ID[pl]] = outs[(mej, pl)].data_ptr()
+    ws = torch.empty(ops.enhance_volumes_workspace_bytes(1, X, Y, Z), dtype=torch.uint8, device=cuda_device)
+    L.check(L.load().msl_enhance_volumes(vol.data_ptr(), 1, X, Y, Z, ptrs, ops.device_tables(cuda_device).data_ptr(),
+                                         ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+    for mej, pl in want:
+        assert torch.equal(outs[(mej, pl)][0], ops.enhance_slices(vol, mej, pl, layout="P")), (mej, pl)
+
+
 def test_volume_mode_custom_tables(ops, torch_mod, cuda_device):
     """The table block is a parameter: any non-decreasing LUT_L must work (the volume path folds gray histograms into
     L histograms through it).  This one starts above 0, folds up to four grays into one L and leaves gaps."""
