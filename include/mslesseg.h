@@ -149,6 +149,20 @@ size_t msl_png_bytes(int H, int W, int channels);
 int msl_png_pack(const uint8_t* pixels, int n, int H, int W, int channels,
                  uint8_t* out, size_t out_pitch_bytes, msl_stream_t stream);
 
+/* ---- host hand-off helpers: copy only the non-zero box of a result ------------------------------
+ * Skull-stripped volumes are two thirds background and predicted masks ~99 % zeros, and the device-to-host copy of the
+ * results is what bounds the path end to end.  msl_nonzero_flags marks which slices (a) and rows (b) of a uint8 stack
+ * [nvol][A][B][C] hold a non-zero byte (any_a [nvol][A], any_b [nvol][B], overwritten); msl_copy_box_d2h copies the box
+ * a0 <= a < a1, b0 <= b < b1 (full rows of C bytes) of ONE [A][B][C] array from the device to a host array of the same
+ * shape (cudaMemcpy2DAsync); the caller keeps the rest of the host array zero. */
+int msl_nonzero_flags(const uint8_t* stack, int nvol, int A, int B, int C,
+                      uint8_t* any_a, uint8_t* any_b, msl_stream_t stream);
+int msl_copy_box_d2h(void* host_dst, const uint8_t* dev_src, int A, int B, int C,
+                     int a0, int a1, int b0, int b1, msl_stream_t stream);
+/* the same for nvol consecutive arrays; boxes: HOST array [nvol][4] = {a0, a1, b0, b1} */
+int msl_copy_boxes_d2h(void* host_dst, const uint8_t* dev_src, int nvol, int A, int B, int C,
+                       const int32_t* boxes, msl_stream_t stream);
+
 /* ---- E7 helper: verificar_grises (utils/utils.py:421-427) on 3-channel images ------------------
  * cv2.cvtColor(BGR2GRAY) in OpenCV's 8-bit fixed point: (3735 B + 19235 G + 9798 R + 2^14) >> 15.
  * bgr: uint8 [npx][3] interleaved, gray: uint8 [npx]. */

@@ -542,6 +542,35 @@ def test_png_pack_matches_container_oracle(ops, torch_mod, cuda_device, shape):
         ops.png_pack(torch.zeros((1, 400, 300, 4), dtype=torch.uint8, device=cuda_device))    # 480 KB: refused, not mangled
 
 
+def test_nonzero_box_hand_off(ops, torch_mod, cuda_device):
+    """Results can travel to the host as their non-zero boxes: flags, box copy and the host mirror (ops.HostResult)."""
+    torch = torch_mod
+    rng = np.random.default_rng(4)
+    nvol, A, B, C = 3, 19, 23, 30
+    a = np.zeros((nvol, A, B, C), dtype=np.uint8)
+    a[0, 4:11, 6:15, 3:20] = rng.integers(0, 256, (7, 9, 17))
+    a[0, 4, 6, 5] = 9; a[0, 10, 14, 7] = 1                     # corners of the box are really non-zero
+    a[2, :, :, 29] = 7                                          # full box
+    dev = torch.from_numpy(a).to(cuda_device)
+    fa, fb = ops.nonzero_flags(dev)
+    assert np.array_equal(fa.cpu().numpy(), (a.reshape(nvol, A, -1).max(axis=2) > 0).astype(np.uint8))
+    assert np.array_equal(fb.cpu().numpy(), (a.transpose(0, 2, 1, 3).reshape(nvol, B, -1).max(axis=2) > 0).astype(np.uint8))
+    assert ops.box_from_flags(fa[0].cpu().numpy(), fb[0].cpu().numpy()) == (4, 11, 6, 15)
+    assert ops.box_from_flags(fa[1].cpu().numpy(), fb[1].cpu().numpy()) == (0, 0, 0, 0)
+    h = ops.HostResult((nvol, A, B, C))
+    moved = h.update(0, dev, fa.cpu().numpy(), fb.cpu().numpy())
+    torch.cuda.synchronize()
+    assert np.array_equal(h.host.numpy(), a) and moved == 7 * 9 * C + A * B * C
+    # a different result with a smaller box: the stale margin is cleared on the host
+    b = np.zeros_like(a)
+    b[0, 5:7, 8:9, :] = 3
+    devb = torch.from_numpy(b).to(cuda_device)
+    fa, fb = ops.nonzero_flags(devb)
+    h.update(0, devb, fa.cpu().numpy(), fb.cpu().numpy())
+    torch.cuda.synchronize()
+    assert np.array_equal(h.host.numpy(), b)
+
+
 def test_no_cpu_fallback(ops, torch_mod):
     torch = torch_mod
     with pytest.raises(TypeError):

@@ -285,6 +285,35 @@ int msl_png_pack(const uint8_t* pixels, int n, int H, int W, int channels, uint8
     return launch_png_pack(pixels, n, H, W, channels, out, out_pitch_bytes, (cudaStream_t)stream);
 }
 
+int msl_nonzero_flags(const uint8_t* stack, int nvol, int A, int B, int C, uint8_t* any_a, uint8_t* any_b, msl_stream_t stream) {
+    MSL_REQUIRE(stack && any_a && any_b, "NULL pointer");
+    MSL_REQUIRE(nvol > 0 && A > 0 && B > 0 && C > 0, "non-positive size");
+    MSL_REQUIRE(nvol <= 65535, "at most 65535 volumes per call");
+    return launch_nonzero_flags(stack, nvol, A, B, C, any_a, any_b, (cudaStream_t)stream);
+}
+
+int msl_copy_box_d2h(void* host_dst, const uint8_t* dev_src, int A, int B, int C, int a0, int a1, int b0, int b1, msl_stream_t stream) {
+    MSL_REQUIRE(host_dst && dev_src, "NULL pointer");
+    MSL_REQUIRE(A > 0 && B > 0 && C > 0, "non-positive size");
+    MSL_REQUIRE(0 <= a0 && a0 <= a1 && a1 <= A && 0 <= b0 && b0 <= b1 && b1 <= B, "box [%d, %d) x [%d, %d) outside [0, %d) x [0, %d)", a0, a1, b0, b1, A, B);
+    if (a0 == a1 || b0 == b1) return MSL_OK;
+    const size_t pitch = (size_t)B * C, off = ((size_t)a0 * B + b0) * C;
+    MSL_CUDA_CHECK(cudaMemcpy2DAsync(static_cast<uint8_t*>(host_dst) + off, pitch, dev_src + off, pitch, (size_t)(b1 - b0) * C,
+                                     (size_t)(a1 - a0), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return MSL_OK;
+}
+
+int msl_copy_boxes_d2h(void* host_dst, const uint8_t* dev_src, int nvol, int A, int B, int C, const int32_t* boxes, msl_stream_t stream) {
+    MSL_REQUIRE(boxes && nvol >= 0, "NULL boxes / negative count");
+    const size_t vol = (size_t)A * B * C;
+    for (int v = 0; v < nvol; ++v) {
+        const int rc = msl_copy_box_d2h(static_cast<uint8_t*>(host_dst) + v * vol, dev_src + v * vol, A, B, C,
+                                        boxes[4 * v], boxes[4 * v + 1], boxes[4 * v + 2], boxes[4 * v + 3], stream);
+        if (rc) return rc;
+    }
+    return MSL_OK;
+}
+
 int msl_bgr_to_gray(const uint8_t* bgr, size_t npx, uint8_t* gray, msl_stream_t stream) {
     if (npx == 0) return MSL_OK;
     MSL_REQUIRE(bgr && gray, "NULL pointer");

@@ -25,7 +25,8 @@ enum KernelKind {
     K_SLICE_COUNTS = 21,  // per-slice confusion counts of the three planes
     K_BGR2GRAY = 22,
     K_PNG_PACK = 23,
-    K_NKIND = 24
+    K_NONZERO_FLAGS = 24,
+    K_NKIND = 25
 };
 
 // RAII: counts the launch and, when profiling is enabled, brackets it with CUDA events on `stream`.
@@ -110,6 +111,7 @@ int launch_combine_predictions(const float* masks, const int32_t* inst_offset, i
 int launch_bgr_to_gray(const uint8_t* bgr, size_t npx, uint8_t* gray, cudaStream_t stream);
 size_t png_file_bytes(int H, int W, int ch);
 int launch_png_pack(const uint8_t* pixels, int n, int H, int W, int ch, uint8_t* out, size_t out_pitch, cudaStream_t stream);
+int launch_nonzero_flags(const uint8_t* stack, int nvol, int A, int B, int C, uint8_t* any_a, uint8_t* any_b, cudaStream_t stream);
 int launch_slice_counts(const uint8_t* gt, const uint8_t* pred, int nvol, int X, int Y, int Z, long long* counts, cudaStream_t stream);
 int launch_consensus_eval(const uint8_t* ax, const uint8_t* co, const uint8_t* sa, const uint8_t* gt,
                           int nvol, size_t nvox, int umbral, uint8_t* consenso, long long* counts, cudaStream_t stream);

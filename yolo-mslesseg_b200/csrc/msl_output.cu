@@ -666,6 +666,32 @@ __global__ void slice_counts_finalize_kernel(long long* counts, int nvol, int X,
     c[3] = n - c[0] - c[1] - c[2] - c[3];
 }
 
+// Which slices (a) and which rows (b) of a uint8 stack [nvol][A][B][C] hold a non-zero byte: the bounding box that a
+// host copy needs (everything outside it is zero).  grid (A, nvol); a warp per row, 32-bit loads where the row allows.
+// any_a [nvol][A] and any_b [nvol][B] are pre-zeroed; every writer stores 1.
+__global__ void __launch_bounds__(256) nonzero_flags_kernel(const uint8_t* __restrict__ stack, int A, int B, int C,
+                                                            uint8_t* __restrict__ any_a, uint8_t* __restrict__ any_b) {
+    const int ia = blockIdx.x, v = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint8_t* sl = stack + ((size_t)v * A + ia) * (size_t)B * C;
+    bool any = false;
+    for (int b = warp; b < B; b += 8) {
+        const uint8_t* row = sl + (size_t)b * C;
+        uint32_t acc = 0;
+        const int head = min(C, (int)((4 - (reinterpret_cast<uintptr_t>(row) & 3)) & 3));
+        const int nw = (C - head) >> 2;
+        const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row + head);
+        for (int q = lane; q < nw; q += 32) acc |= __ldg(row4 + q);
+        for (int o = lane; o < head; o += 32) acc |= row[o];
+        for (int o = head + 4 * nw + lane; o < C; o += 32) acc |= row[o];
+        if (__any_sync(FULL, acc != 0)) {
+            any = true;
+            if (lane == 0) any_b[(size_t)v * B + b] = 1;
+        }
+    }
+    if (__syncthreads_or(any) && threadIdx.x == 0) any_a[(size_t)v * A + ia] = 1;
+}
+
 inline bool aligned8(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
 
 inline int chunks_for(size_t nvox, int nvol) {
@@ -781,6 +807,15 @@ int launch_slice_counts(const uint8_t* gt, const uint8_t* pred, int nvol, int X,
     const size_t n = (size_t)nvol * nsl;
     slice_counts_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(counts, nvol, X, Y, Z);
     MSL_LAUNCH_CHECK("slice_counts_finalize_kernel");
+    return MSL_OK;
+}
+
+int launch_nonzero_flags(const uint8_t* stack, int nvol, int A, int B, int C, uint8_t* any_a, uint8_t* any_b, cudaStream_t stream) {
+    MSL_CUDA_CHECK(cudaMemsetAsync(any_a, 0, (size_t)nvol * A, stream));
+    MSL_CUDA_CHECK(cudaMemsetAsync(any_b, 0, (size_t)nvol * B, stream));
+    ProfScope prof(K_NONZERO_FLAGS, stream);
+    nonzero_flags_kernel<<<dim3(A, nvol), 256, 0, stream>>>(stack, A, B, C, any_a, any_b);
+    MSL_LAUNCH_CHECK("nonzero_flags_kernel");
     return MSL_OK;
 }
 

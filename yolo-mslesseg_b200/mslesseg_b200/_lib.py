@@ -43,6 +43,9 @@ _SIGNATURES = {
     "msl_enhance_volumes": (C.c_int, [_vp, _i, _i, _i, _i, C.POINTER(C.c_void_p), _vp, _vp, _sz, _vp]),
     "msl_png_bytes": (_sz, [_i, _i, _i]),
     "msl_png_pack": (C.c_int, [_vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "msl_nonzero_flags": (C.c_int, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "msl_copy_box_d2h": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "msl_copy_boxes_d2h": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "msl_bgr_to_gray": (C.c_int, [_vp, _sz, _vp, _vp]),
     "msl_combine_predictions": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "msl_recon": (C.c_int, [_vp, _sz, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

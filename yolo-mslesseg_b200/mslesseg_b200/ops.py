@@ -344,3 +344,87 @@ def png_pack(pixels: torch.Tensor):
     out = torch.empty((n, pitch), dtype=torch.uint8, device=pixels.device)
     L.check(L.load().msl_png_pack(_ptr(pixels), n, H, W, ch, _ptr(out), pitch, _stream()))
     return out, size
+
+
+# ------------------------------------------------------------------------------------ host hand-off
+def nonzero_flags(stack: torch.Tensor, out=None):
+    """Which slices and rows of a uint8 stack [nvol, A, B, C] hold a non-zero byte: (any_a [nvol, A], any_b [nvol, B]).
+    out: optional pair of contiguous uint8 device tensors of those shapes (e.g. views of one buffer that goes to the host
+    in a single copy)."""
+    _need_cuda(stack, "stack")
+    if stack.dtype != torch.uint8 or stack.dim() != 4 or not stack.is_contiguous():
+        raise ValueError("stack must be a contiguous uint8 tensor [nvol, A, B, C]")
+    nvol, A, B, Cc = (int(d) for d in stack.shape)
+    if out is None:
+        any_a = torch.empty((nvol, A), dtype=torch.uint8, device=stack.device)
+        any_b = torch.empty((nvol, B), dtype=torch.uint8, device=stack.device)
+    else:
+        any_a, any_b = out
+        _need_cuda(any_a, "out[0]")
+        _need_cuda(any_b, "out[1]")
+        if tuple(any_a.shape) != (nvol, A) or tuple(any_b.shape) != (nvol, B) or any_a.dtype != torch.uint8 or any_b.dtype != torch.uint8:
+            raise ValueError("out must be uint8 tensors [nvol, A] and [nvol, B]")
+    L.check(L.load().msl_nonzero_flags(_ptr(stack), nvol, A, B, Cc, _ptr(any_a), _ptr(any_b), _stream()))
+    return any_a, any_b
+
+
+def box_from_flags(any_a: np.ndarray, any_b: np.ndarray):
+    """(a0, a1, b0, b1) of one volume from its host-side flags; an empty box is (0, 0, 0, 0)."""
+    ia, ib = np.flatnonzero(any_a), np.flatnonzero(any_b)
+    if ia.size == 0 or ib.size == 0:
+        return (0, 0, 0, 0)
+    return (int(ia[0]), int(ia[-1]) + 1, int(ib[0]), int(ib[-1]) + 1)
+
+
+def copy_box_to_host(dev: torch.Tensor, host: torch.Tensor, box) -> int:
+    """Asynchronous device-to-host copy (current stream) of the box (a0, a1, b0, b1) - full rows - of ONE uint8 array
+    [A, B, C] into a (pinned) host array of the same shape; the rest of `host` is left alone (the caller keeps it zero).
+    Returns the number of bytes copied."""
+    _need_cuda(dev, "dev")
+    if dev.dtype != torch.uint8 or dev.dim() != 3 or not dev.is_contiguous():
+        raise ValueError("dev must be a contiguous uint8 tensor [A, B, C]")
+    if host.device.type != "cpu" or host.dtype != torch.uint8 or tuple(host.shape) != tuple(dev.shape) or not host.is_contiguous():
+        raise ValueError("host must be a contiguous uint8 CPU tensor of the same shape")
+    A, B, Cc = (int(d) for d in dev.shape)
+    a0, a1, b0, b1 = (int(v) for v in box)
+    L.check(L.load().msl_copy_box_d2h(host.data_ptr(), _ptr(dev), A, B, Cc, a0, a1, b0, b1, _stream()))
+    return (a1 - a0) * (b1 - b0) * Cc
+
+
+class HostResult:
+    """A pinned host array [nvol, A, B, C] that mirrors device results while receiving only their non-zero boxes.
+    Successive updates of the same volumes may be in flight together; only when a box shrinks (stale data must be zeroed
+    on the host) does `update` wait for the earlier copy of that volume."""
+
+    def __init__(self, shape):
+        self.host = torch.zeros(tuple(int(d) for d in shape), dtype=torch.uint8).pin_memory()
+        self.boxes = [(0, 0, 0, 0)] * int(shape[0])
+        self.events = [None] * int(shape[0])
+
+    def update(self, v0: int, dev_stack: torch.Tensor, any_a: np.ndarray, any_b: np.ndarray) -> int:
+        """Volumes v0 .. v0+n of the host array := dev_stack [n, A, B, C], given its host-side non-zero flags.
+        Copies are enqueued on the current stream; returns the bytes they move."""
+        _need_cuda(dev_stack, "dev_stack")
+        n = int(dev_stack.shape[0])
+        if dev_stack.dtype != torch.uint8 or tuple(dev_stack.shape[1:]) != tuple(self.host.shape[1:]) or v0 < 0 or v0 + n > self.host.shape[0]:
+            raise ValueError("dev_stack must be uint8 [n, A, B, C] and fit the host array")
+        A, B, Cc = (int(d) for d in self.host.shape[1:])
+        boxes = np.zeros((n, 4), dtype=np.int32)
+        moved = 0
+        for i in range(n):
+            box = box_from_flags(any_a[i], any_b[i])
+            old = self.boxes[v0 + i]
+            if old[1] > old[0] and not (box[0] <= old[0] and old[1] <= box[1] and box[2] <= old[2] and old[3] <= box[3]):
+                if self.events[v0 + i] is not None:
+                    self.events[v0 + i].synchronize()                        # the earlier copy into this volume has landed
+                self.host[v0 + i, old[0]:old[1], old[2]:old[3]] = 0          # stale non-zero data outside the new box
+            self.boxes[v0 + i] = box
+            boxes[i] = box
+            moved += (box[1] - box[0]) * (box[3] - box[2]) * Cc
+        L.check(L.load().msl_copy_boxes_d2h(self.host[v0].data_ptr(), _ptr(dev_stack), n, A, B, Cc,
+                                            boxes.ctypes.data_as(C.c_void_p), _stream()))
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        for i in range(n):
+            self.events[v0 + i] = ev
+        return moved
