@@ -53,6 +53,33 @@ def test_argument_errors_without_gpu():
         _lib.check(rc)
 
 
+def test_argument_errors_of_the_widened_entry_points_without_gpu():
+    lib = _lib.load()
+    P = ctypes.c_void_p(4096)
+    assert lib.msl_png_bytes(218, 182, 4) == 159000 and lib.msl_png_bytes(33, 21, 1) == 794 and lib.msl_png_bytes(5, 5, 3) == 0
+    assert lib.msl_png_pack(P, 1, 218, 182, 3, P, 160000, None) == _lib.ERR_ARG and b"channels" in lib.msl_last_error()
+    assert lib.msl_png_pack(P, 1, 218, 182, 4, P, 1000, None) == _lib.ERR_ARG and b"pitch" in lib.msl_last_error()
+    assert lib.msl_png_pack(None, 0, 218, 182, 4, None, 0, None) == 0                       # nothing to do
+    assert lib.msl_combine_predictions(P, P, 1, 640, 544, 182, 218, _lib.OUT_PNG_RGBA, P, None) == _lib.ERR_ARG
+    assert b"layout" in lib.msl_last_error()
+    assert lib.msl_combine_predictions(None, None, 0, 1, 1, 182, 218, _lib.OUT_G, None, None) == 0
+    assert lib.msl_slice_counts(P, None, 1, 8, 8, 8, P, None) == _lib.ERR_ARG and b"NULL" in lib.msl_last_error()
+    assert lib.msl_copy_box_d2h(P, P, 10, 10, 10, 3, 2, 0, 10, None) == _lib.ERR_ARG and b"box" in lib.msl_last_error()
+    assert lib.msl_copy_box_d2h(P, P, 10, 10, 10, 2, 2, 0, 10, None) == 0                   # empty box: no copy issued
+    assert lib.msl_nonzero_flags(P, 1, 0, 4, 4, P, P, None) == _lib.ERR_ARG
+    assert lib.msl_bgr_to_gray(None, 0, None, None) == 0
+
+
+def test_host_box_logic():
+    from mslesseg_b200 import ops
+    a = np.zeros(10, np.uint8); b = np.zeros(7, np.uint8)
+    assert ops.box_from_flags(a, b) == (0, 0, 0, 0)
+    a[3] = a[8] = 1; b[0] = 1
+    assert ops.box_from_flags(a, b) == (3, 9, 0, 1)
+    b[:] = 0
+    assert ops.box_from_flags(a, b) == (0, 0, 0, 0)
+
+
 def test_tables():
     t = T.host_tables()
     assert t.shape == (T.TABLES_BYTES,)
