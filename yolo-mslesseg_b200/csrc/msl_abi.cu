@@ -79,6 +79,11 @@ static size_t u_stack_bytes_per_volume(int X, int Y, int Z) {
     return ((ax + 255) & ~(size_t)255) + ((co + 255) & ~(size_t)255) + ((sa + 255) & ~(size_t)255);
 }
 
+// per-plane table blocks of the dense kernel (three planes)
+static size_t dense_tabs_total(int X, int Y, int Z) {
+    return ((dense_tabs_bytes(X, Y) + dense_tabs_bytes(X, Z) + dense_tabs_bytes(Y, Z)) + 255) & ~(size_t)255;
+}
+
 static int enhance_chunk_volumes(void) {
     const char* e = getenv("MSL_VOLUME_CHUNK");
     int c = e ? atoi(e) : 32;
@@ -94,7 +99,7 @@ size_t msl_workspace_bytes(int op, int nvol, int X, int Y, int Z) {
             int chunk = enhance_chunk_volumes();
             if (chunk > nvol) chunk = nvol;
             (void)N;
-            return stats + (size_t)chunk * u_stack_bytes_per_volume(X, Y, Z);
+            return stats + (size_t)chunk * u_stack_bytes_per_volume(X, Y, Z) + dense_tabs_total(X, Y, Z);
         }
         case MSL_WS_RECON: {
             int m = X > Y ? X : Y;
@@ -189,6 +194,8 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z, uint8_t
     // staged normalised stacks, PNG orientation, slice pitch padded to 16 bytes: [chunk][n_p][u_pitch]
     size_t upitch[3];
     uint8_t* U[3];
+    uint8_t* dtabs = nullptr;                       // per-plane tables of the dense kernel
+    const size_t dtabs_bytes = dense_tabs_total(X, Y, Z);
     {
         uint8_t* cur = reinterpret_cast<uint8_t*>(ws) + stats_bytes;
         for (int pl = 0; pl < 3; ++pl) {
@@ -196,6 +203,7 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z, uint8_t
             U[pl] = cur;
             cur += (((size_t)n_p[pl] * upitch[pl] + 255) & ~(size_t)255) * (size_t)chunk;
         }
+        dtabs = cur;
     }
 
     int rc = launch_init_stats(stats, nsl, stream);
@@ -236,7 +244,7 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z, uint8_t
                 // the planes of the chunk share one launch (one grid tail instead of three) when they agree on CLAHE
                 const bool cl = dst[MSL_MEJORA_CLAHE] != nullptr;
                 if (ndense > 0 && cl != dense_cl) {
-                    rc = launch_enhance_dense_multi(dplanes, ndense, tables, stream);
+                    rc = launch_enhance_dense_multi(dplanes, ndense, tables, dtabs, dtabs_bytes, stream);
                     if (rc) return rc;
                     ndense = 0;
                 }
@@ -261,7 +269,7 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z, uint8_t
             }
         }
         if (ndense > 0) {
-            rc = launch_enhance_dense_multi(dplanes, ndense, tables, stream);
+            rc = launch_enhance_dense_multi(dplanes, ndense, tables, dtabs, dtabs_bytes, stream);
             if (rc) return rc;
         }
     }

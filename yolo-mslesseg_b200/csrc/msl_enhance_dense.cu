@@ -10,10 +10,14 @@
 //         densely packed, same orientation.  One CTA per slice; all enhancements share one shared-memory copy.
 //
 // The kernel moves 2-5 B per pixel but is bound by shared-memory latency and instruction issue, so:
-//  * ONE set of histograms: 64 tile histograms over u, one 32-bit word per bin (packed 16-bit bins double the cost of
-//    the shared-memory atomics, profiles/microbench).  HE's global histogram is their sum; CLAHE's histograms over
-//    L = LUT_L[u] are segment sums of the u-bins (LUT_L is monotone).  A thread walks one P column (constant tile
-//    row) in segments of constant tile column, so the histogram base is hoisted out of the pixel loop.
+//  * Tile LUTs are built by autonomous warps (round 2): a warp pulls a tile from a queue, counts the tile's pixels into its
+//    OWN 1 KB histogram (32-bit bins over u, background never counted), adds it to HE's histogram, adds the
+//    BORDER_REFLECT_101 padding, folds the u-bins into L-bins (LUT_L is monotone), clips, redistributes and writes the
+//    256-byte LUT - no block barrier between those steps, tiles without brain take a per-plane constant LUT, and the
+//    histogram scratch is 16 KB instead of 64 KB.  Round 1 ran these as five block-wide phases (a sixth of the kernel was
+//    barrier waits).
+//  * Everything that depends only on the plane geometry (fold table, blend weights / offsets, the blank-tile LUT, the
+//    blank-slice constant) is computed once per launch by dense_tables_kernel and copied into shared memory.
 //  * HE / GC / LT are applied through one packed 32-bit table (one lookup per pixel for all three) and transposed
 //    into three output words with PRMT.
 //  * CLAHE tile LUTs are composed with LUT_L once per slice into "pair tables": for each tile row and gray the 9
@@ -41,10 +45,10 @@ struct DenseParams {
     uint8_t* out_lt;
     size_t out_pitch;          // bytes between output slices (= npx)
     const uint8_t* tables;
+    const uint8_t* ptabs;      // per-plane tables written by dense_tables_kernel (CLAHE only)
     int rows, cols;            // slice orientation (G); P is cols x rows
     int th, tw, clip;
     float lut_scale;
-    unsigned magic_w;          // floor(2^32 / rows) + 1 : o / rows == umulhi(o, magic_w) for o < 2^32 / rows
 };
 
 __device__ __forceinline__ int reflect101(int p, int len) {
@@ -56,20 +60,28 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 // shared memory map (bytes)
 constexpr int kOffLutL = 0;        // [256] LUT_L
 constexpr int kOffLutOut = 256;    // [256] LUT_OUT
-constexpr int kOffUstart = 512;    // u16[257] first u whose LUT_L[u] >= L     (514 B -> pad to 528)
-constexpr int kOffT3 = 1040;       // u32[256] he | gc << 8 | lt << 16
-constexpr int kOffHeHist = 2064;   // u32[256]
-constexpr int kOffMisc = 3088;     // int[32]
-constexpr int kOffFold = 3216;     // u32[256] byte offsets of the (up to) two u-bins that fold into L-bin L: lo16 | hi16
-constexpr int kOffTabs = 4240;     // xw[cols] f32 | xo[cols] u32 | yw[rows] f32 | yo[rows] u32 | R | su[npx16]
+constexpr int kOffT3 = 512;        // u32[256] he | gc << 8 | lt << 16
+constexpr int kOffHeHist = 1536;   // u32[256]
+constexpr int kOffMisc = 2560;     // int[32]
+constexpr int kOffPT = 2688;       // per-plane tables (copy of the global block, layout below)
+// per-plane table block (dense_tables_kernel); offsets relative to the block
+constexpr int kPTFold = 0;         // u32[256] byte offsets of the (up to) two u-bins that fold into L-bin L: lo16 | hi16
+constexpr int kPTUstart = 1024;    // u16[257] first u whose LUT_L[u] >= L   (514 B -> padded to 528)
+constexpr int kPTProto = 1552;     // u8[256] tile LUT of a tile without brain: histogram {LUT_L[0]: th * tw}
+constexpr int kPTMisc = 1808;      // int[4]: [0] long folds (some L-bin sums more than two u-bins), [1] CLAHE value of a blank slice
+constexpr int kPTW = 1824;         // xw[cols] f32 | xo[cols] u32 | yw[rows] f32 | yo[rows] u32
 constexpr int kPairTy = 256 * 20;          // bytes of pair tables per tile row: 256 grays x (9 pairs x 2 B, padded to 20)
-constexpr int kPairStride = kPairTy + 1024;   // each tile row's pair tables are followed by its background row TZ[ty][r] (<= 256 floats)
-constexpr int kPairBytes = 8 * kPairStride;   // 49,152
-constexpr int kHistBytes = 64 * 256 * 4;        // 64 tile histograms, one 32-bit word per bin (packed 16-bit bins make two grays
-                                                // share a word and double the cost of the shared-memory atomics: profiles/microbench)
-constexpr int kRBytes = kHistBytes;             // R: tile histograms (64 KB), later pair tables + background rows (48 KB) + tile LUTs (16 KB)
+constexpr int kPairStride = kPairTy + 1024 + 4;   // each tile row's pair tables are followed by its background row TZ[ty][r] (<= 256 floats);
+                                                  // + 4: consecutive tile rows start one bank apart (a warp reads TZ of two tile rows at one r)
+constexpr int kPairBytes = (8 * kPairStride + 15) & ~15;   // 49,184
+constexpr int kRBytes = kPairBytes + 64 * 256;  // R: pair tables + background rows, then the 64 tile LUTs Tc[tile][L]; while the tile LUTs
+                                                // are built the head of R holds one 1 KB histogram per warp
+static_assert(kWarps * 1024 <= kPairBytes, "histogram scratch must fit in front of the tile LUTs");
 
-__device__ __forceinline__ void add_hist(unsigned* ht, int bin) { if (bin) atomicAdd(&ht[bin], 1u); }   // bin 0 is implicit
+// tiles in centre-first order: the tiles with the most brain are pulled first, the cheap border tiles fill the tail
+__constant__ uint8_t kTileOrder[64] = {27, 28, 35, 36, 19, 20, 26, 29, 34, 37, 43, 44, 18, 21, 42, 45, 11, 12, 25, 30, 33, 38,
+                                       51, 52, 10, 13, 17, 22, 41, 46, 50, 53, 3,  4,  9,  14, 24, 31, 32, 39, 49, 54, 59, 60,
+                                       2,  5,  16, 23, 40, 47, 58, 61, 1,  6,  8,  15, 48, 55, 57, 62, 0,  7,  56, 63};
 
 // floor(a / b) for 0 <= a < 2^16, 1 <= b <= 256 without the integer-division sequence: the approximate quotient is biased
 // up by 4e-6 (more than its error, less than the 1 / b gap below the next integer).
@@ -102,36 +114,140 @@ struct DenseLaunch {
     int first[4];
 };
 
-template <bool DO_CLAHE>
-__global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const __grid_constant__ DenseLaunch L) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int plane_k = (int)blockIdx.x >= L.first[2] ? 2 : ((int)blockIdx.x >= L.first[1] ? 1 : 0);
-    const DenseParams& p = L.plane[plane_k];
+// OpenCV CLAHE_CalcLut_Body for one tile whose 256 L-bins are spread over a warp, 8 consecutive bins per lane: clip,
+// redistribute the excess (residualStep walk), CDF, LUT = saturate_cast<uchar>(cdf * lutScale).  Returns the lane's 8 LUT bytes.
+__device__ __forceinline__ uint2 clip_cdf_tile(int (&hb)[8], int lane, int clip, float lut_scale) {
+    int clipped = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (hb[k] > clip) { clipped += hb[k] - clip; hb[k] = clip; }
+    clipped = warp_sum(clipped);
+    const int rb = clipped >> 8;
+    const int res = clipped & 255;
+    // residual: bins 0, step, 2*step, ... (res of them) get one more; walk this lane's 8 bins without dividing per bin
+    const int step = res > 0 ? small_div(256, res) : 256;
+    const int base = lane * 8;
+    int kn = small_div(base + step - 1, step);          // index of the first multiple of step that is >= base
+    int nxt = kn * step;
+    int run = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        hb[k] += rb;
+        const bool hit = (nxt == base + k) && (kn < res);
+        if (hit) { hb[k] += 1; nxt += step; ++kn; }
+        run += hb[k];
+        hb[k] = run;
+    }
+    const int excl = warp_incl_scan(run, lane) - run;
+    // saturate_cast<uchar>(cdf * lutScale): the product lies in [0, 255.0001], so int -> float and round-half-even both
+    // go through magic adds and the low byte of the sum is the result
+    uint32_t o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float cdf = __fsub_rn(__uint_as_float(0x4b000000u + (uint32_t)(hb[k] + excl)), 8388608.0f);
+        o[k] = __float_as_uint(__fadd_rn(__fmul_rn(cdf, lut_scale), 12582912.0f));
+    }
+    const uint32_t lo = __byte_perm(__byte_perm(o[0], o[1], 0x0040), __byte_perm(o[2], o[3], 0x0040), 0x5410);
+    const uint32_t hi = __byte_perm(__byte_perm(o[4], o[5], 0x0040), __byte_perm(o[6], o[7], 0x0040), 0x5410);
+    return make_uint2(lo, hi);
+}
+
+// Everything that depends only on the plane (geometry + LUT_L): one CTA of 288 threads per stack, once per launch.
+__global__ void __launch_bounds__(288) dense_tables_kernel(const __grid_constant__ DenseLaunch L) {
+    __shared__ uint8_t lutl[256];
+    __shared__ uint16_t ustart[257];
+    const DenseParams& p = L.plane[blockIdx.x];
+    uint8_t* tb = const_cast<uint8_t*>(p.ptabs);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int rows = p.rows, cols = p.cols, th = p.th, tw = p.tw;
+    if (tid < 256) lutl[tid] = __ldg(p.tables + MSL_TAB_LUT_L + tid);
+    if (tid == 0) reinterpret_cast<int*>(tb + kPTMisc)[0] = 0;
+    __syncthreads();
+    if (tid <= 256) {
+        // LUT_L is monotone: the u-bins that fold into L-bin L are [ustart[L], ustart[L+1])
+        int lo = 0, hi = 256;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)lutl[mid] >= tid) hi = mid; else lo = mid + 1; }
+        ustart[tid] = (uint16_t)lo;
+        reinterpret_cast<uint16_t*>(tb + kPTUstart)[tid] = (uint16_t)lo;
+    }
+    __syncthreads();
+    if (tid < 256) {
+        // fold table: L-bin tid sums u-bins [ustart, ustart + n).  n <= 2 for cv2's LUT_L: keep two byte offsets, the
+        // unused ones pointing at u-bin 0, which is never counted and stays zero.  n > 2 (other tables): generic loop.
+        const int u0 = ustart[tid], n = (int)ustart[tid + 1] - u0;
+        reinterpret_cast<uint32_t*>(tb + kPTFold)[tid] = (uint32_t)(n > 0 ? u0 * 4 : 0) | ((uint32_t)(n > 1 ? (u0 + 1) * 4 : 0) << 16);
+        if (n > 2) reinterpret_cast<int*>(tb + kPTMisc)[0] = 1;
+    }
+    // interpolation tables (OpenCV CLAHE_Interpolation_Body): blend weight + table offsets per P row / P column.
+    //   P row r    (slice column b): weight xa, pair slot j = floor(txf) + 1 in [0, 8]  -> byte offset 2*j
+    //   P column c (slice row a)   : weight ya, tile rows ty1 / ty2
+    {
+        float* xw = reinterpret_cast<float*>(tb + kPTW);
+        uint32_t* xo = reinterpret_cast<uint32_t*>(xw + cols);
+        float* yw = reinterpret_cast<float*>(xo + cols);
+        uint32_t* yo = reinterpret_cast<uint32_t*>(yw + rows);
+        const float inv_tw = __fdiv_rn(1.0f, (float)tw), inv_th = __fdiv_rn(1.0f, (float)th);
+        for (int r = tid; r < cols; r += blockDim.x) {
+            const int b = cols - 1 - r;
+            const float txf = __fsub_rn(__fmul_rn((float)b, inv_tw), 0.5f);
+            const int t1 = (int)floorf(txf);
+            xw[r] = __fsub_rn(txf, (float)t1);
+            xo[r] = (uint32_t)(2 * (min(max(t1, -1), 7) + 1));
+        }
+        for (int a = tid; a < rows; a += blockDim.x) {
+            const float tyf = __fsub_rn(__fmul_rn((float)a, inv_th), 0.5f);
+            const int t1 = (int)floorf(tyf), t2 = t1 + 1;
+            yw[a] = __fsub_rn(tyf, (float)t1);
+            yo[a] = (uint32_t)max(t1, 0) | ((uint32_t)min(t2, 7) << 16);
+        }
+    }
+    // A tile without brain holds th * tw pixels of gray 0: its LUT is a constant of the plane.  A blank slice is 64 such
+    // tiles; the blend of four equal tile values z is z after rounding, so every pixel is LUT_OUT[T[LUT_L[0]]].
+    if (tid < 32) {
+        const int L0 = lutl[0];
+        int hb[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hb[k] = (lane * 8 + k == L0) ? th * tw : 0;
+        const uint2 t = clip_cdf_tile(hb, lane, p.clip, p.lut_scale);
+        reinterpret_cast<uint2*>(tb + kPTProto)[lane] = t;
+        if (lane == (L0 >> 3)) {
+            const uint32_t w = (L0 & 4) ? t.y : t.x;
+            reinterpret_cast<int*>(tb + kPTMisc)[1] = (int)__ldg(p.tables + MSL_TAB_LUT_OUT + ((w >> (8 * (L0 & 3))) & 0xffu));
+        }
+    }
+}
+
+// W_CT: the P row length (= slice rows) as a compile-time constant for the MSLesSeg planes (182, 218), 0 = run time.  With
+// it the row-strided accesses of the histogram and blend loops (px[i * W], op[i * W]) are immediate offsets.
+template <bool DO_CLAHE, int W_CT>
+__device__ __forceinline__ void dense_slice(const DenseParams& p, const size_t s, uint8_t* smem) {
     uint8_t* lutl = smem + kOffLutL;
     uint8_t* lutout = smem + kOffLutOut;
-    uint16_t* ustart = reinterpret_cast<uint16_t*>(smem + kOffUstart);
     uint32_t* t3 = reinterpret_cast<uint32_t*>(smem + kOffT3);
     unsigned* he_hist = reinterpret_cast<unsigned*>(smem + kOffHeHist);
-    int* misc = reinterpret_cast<int*>(smem + kOffMisc);       // [0] i0, [1..16] warp scan totals, [20] blank-slice value, [21] long folds
-    uint32_t* fold = reinterpret_cast<uint32_t*>(smem + kOffFold);
+    int* misc = reinterpret_cast<int*>(smem + kOffMisc);       // [0] i0, [1..8] warp scan totals, [22] tile queue
+    uint8_t* pt = smem + kOffPT;
+    const uint32_t* fold = reinterpret_cast<const uint32_t*>(pt + kPTFold);
+    const uint16_t* ustart = reinterpret_cast<const uint16_t*>(pt + kPTUstart);
+    const int* ptmisc = reinterpret_cast<const int*>(pt + kPTMisc);
     const int rows = p.rows, cols = p.cols, npx = rows * cols;
-    const int W = rows;                                          // P row length
-    float* xw = reinterpret_cast<float*>(smem + kOffTabs);       // indexed by P row r   (slice column b = cols-1-r)
-    uint32_t* xo = reinterpret_cast<uint32_t*>(xw + (DO_CLAHE ? cols : 0));
-    float* yw = reinterpret_cast<float*>(xo + (DO_CLAHE ? cols : 0));   // indexed by P column c (slice row a = c)
-    uint32_t* yo = reinterpret_cast<uint32_t*>(yw + (DO_CLAHE ? rows : 0));
+    const int W = W_CT ? W_CT : rows;                            // P row length
+    const float* xw = reinterpret_cast<const float*>(pt + kPTW);       // indexed by P row r   (slice column b = cols-1-r)
+    const uint32_t* xo = reinterpret_cast<const uint32_t*>(xw + cols);
+    const float* yw = reinterpret_cast<const float*>(xo + cols);         // indexed by P column c (slice row a = c)
+    const uint32_t* yo = reinterpret_cast<const uint32_t*>(yw + rows);
     // (offsets, not pointer casts: an integer round trip would make the compiler fall back to generic LD/ST)
-    const int offR = (kOffTabs + (DO_CLAHE ? (rows + cols) * 8 : 0) + 15) & ~15;
+    const int ptab_bytes = DO_CLAHE ? ((kPTW + (rows + cols) * 8 + 15) & ~15) : 0;
+    const int offR = kOffPT + ptab_bytes;
     uint8_t* R = smem + offR;
     uint8_t* su = R + (DO_CLAHE ? kRBytes : 0);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t s = (size_t)((int)blockIdx.x - L.first[plane_k]);
     const uint8_t* in = p.U + s * p.u_pitch;
     const bool want_he = p.out_he != nullptr, want_lut = want_he || p.out_gc || p.out_lt;
 
     // ---------------------------------------------------------------- load
-    // The slice's 128-bit loads are issued first; the table copies and the histogram clear overlap their latency.
+    // The slice's 128-bit loads are issued first; the table copies overlap their latency.
     constexpr int kMaxVec = 5;                                   // 5 x 16 B per thread in flight (covers 40 KB slices)
     const int nvec = npx >> 4;
     const uint4* in4 = reinterpret_cast<const uint4*>(in);
@@ -143,10 +259,12 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const __grid
     }
     if (tid < 128) reinterpret_cast<uint32_t*>(lutl)[tid] = __ldg(reinterpret_cast<const uint32_t*>(p.tables) + tid);  // LUT_L + LUT_OUT
     if (tid < 256) he_hist[tid] = 0;
-    if (tid == 0) { misc[0] = 256; misc[21] = 0; }
+    if (tid == 0) { misc[0] = 256; misc[22] = 0; }
     if (DO_CLAHE) {
-        uint4* r4 = reinterpret_cast<uint4*>(R);
-        for (int q = tid; q < kHistBytes / 16; q += kThreads) r4[q] = make_uint4(0, 0, 0, 0);
+        // the plane's table block goes global -> shared without passing through registers (cp.async, SASS LDGSTS)
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(pt);
+        for (int q = tid; q < (ptab_bytes >> 4); q += kThreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * (uint32_t)q), "l"(p.ptabs + 16 * (size_t)q) : "memory");
     }
     uint32_t anynz = 0;
     {
@@ -159,44 +277,12 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const __grid
         for (int q = tid + kMaxVec * kThreads; q < nvec; q += kThreads) { const uint4 v = __ldg(in4 + q); su4[q] = v; anynz |= v.x | v.y | v.z | v.w; }
         for (int o = (nvec << 4) + tid; o < npx; o += kThreads) { const uint32_t b = __ldg(in + o); su[o] = (uint8_t)b; anynz |= b; }
     }
+    if (DO_CLAHE) asm volatile("cp.async.wait_all;" ::: "memory");
     // Blank slice (the skull-stripped volumes have ~15 % of them per plane): every output is a constant.
-    // HE: one populated bin -> that bin's index (0); GC_T[0]; LT_T[.][0]; CLAHE: all 64 tiles are identical, their
-    // histogram is {0: tile area}, so the generic clip / redistribute / CDF below is run for ONE tile by warp 0.
+    // HE: one populated bin -> that bin's index (0); GC_T[0]; LT_T[.][0]; CLAHE: the per-plane constant of dense_tables_kernel.
     if (!__syncthreads_or(anynz != 0)) {
-        uint32_t c_he = 0, c_gc = __ldg(p.tables + MSL_TAB_GC), c_lt = __ldg(p.tables + MSL_TAB_LT + 255 * 256), c_cl = 0;
-        if (DO_CLAHE) {
-            if (warp == 0) {
-                const int area = p.th * p.tw, clip = p.clip;
-                // L = LUT_L[0] holds the whole tile
-                const int L0 = lutl[0];
-                int hb[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) hb[k] = (lane * 8 + k == L0) ? area : 0;
-                int clipped = 0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (hb[k] > clip) { clipped += hb[k] - clip; hb[k] = clip; }
-                clipped = warp_sum(clipped);
-                const int rb = clipped / 256, res = clipped - rb * 256;
-                const int step = res > 0 ? max(256 / res, 1) : 256;
-                int run = 0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int bin = lane * 8 + k;
-                    hb[k] += rb;
-                    if (res > 0 && (bin % step) == 0 && (bin / step) < res) hb[k] += 1;
-                    run += hb[k];
-                    hb[k] = run;
-                }
-                const int excl = warp_incl_scan(run, lane) - run;
-                // the blend of four equal tile values z is z after rounding; the pixel value is T[LUT_L[0]]
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (lane * 8 + k == L0) misc[20] = lutout[sat_u8_rn(__fmul_rn((float)(hb[k] + excl), p.lut_scale))];
-            }
-            __syncthreads();
-            c_cl = (uint32_t)misc[20];
-        }
+        const uint32_t c_he = 0, c_gc = __ldg(p.tables + MSL_TAB_GC), c_lt = __ldg(p.tables + MSL_TAB_LT + 255 * 256);
+        const uint32_t c_cl = DO_CLAHE ? (uint32_t)ptmisc[1] : 0u;
         uint8_t* outs[4] = {p.out_he, p.out_clahe, p.out_gc, p.out_lt};
         const uint32_t cv[4] = {c_he, c_cl, c_gc, c_lt};
         const int nw0 = npx >> 2;
@@ -213,48 +299,45 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const __grid
     }
 
     const int th = p.th, tw = p.tw;
-    unsigned* hist = reinterpret_cast<unsigned*>(R);        // 64 tiles x 256 bins
-    uint8_t* tya = smem + kOffTabs;                          // [rows] tile row of every P column (the weight tables that
-                                                             // live here are only written after the histogram pass)
+    uint8_t* Tc = R + kPairBytes;                             // [64][256] tile LUTs
     const uint32_t* su32 = reinterpret_cast<const uint32_t*>(su);
     const int nw = npx >> 2;
 
     if (DO_CLAHE) {
-        // ------------------------------------------------------------ tile histograms over u (real pixels)
-        if (tid <= 256) {
-            // LUT_L is monotone: the u-bins that fold into L-bin L are [ustart[L], ustart[L+1])
-            int lo = 0, hi = 256;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)lutl[mid] >= tid) hi = mid; else lo = mid + 1; }
-            ustart[tid] = (uint16_t)lo;
-        }
-        for (int a = tid; a < rows; a += kThreads) tya[a] = (uint8_t)(a / th);
-        __syncthreads();
-        if (tid < 256) {
-            // fold table: L-bin tid sums u-bins [ustart, ustart + n).  n <= 2 for cv2's LUT_L: keep two byte offsets, the
-            // unused ones pointing at u-bin 0, which is never counted and stays zero.  n > 2 (other tables): generic loop.
-            const int u0 = ustart[tid], n = (int)ustart[tid + 1] - u0;
-            fold[tid] = (uint32_t)(n > 0 ? u0 * 4 : 0) | ((uint32_t)(n > 1 ? (u0 + 1) * 4 : 0) << 16);
-            if (n > 2) misc[21] = 1;
-        }
-        // Column-major walk (same decomposition as the blend): a lane owns one P column (slice row -> its tile row is a
-        // register), the tile column changes only every tw rows and is warp-uniform.  Background pixels (u == 0) are
-        // never counted: every padded tile holds th * tw pixels, so bin 0 is recovered by subtraction in the fold below
-        // (and HE's bin 0 in its CDF); four rows that are background in all 32 columns cost four loads and a branch.
-        {
-            const int nchunk = (W + 31) >> 5;
-            for (int task = warp; task < nchunk * 8; task += kWarps) {
-                const int cc = task % nchunk, tx = 7 - task / nchunk;       // band = the P rows of tile column tx
-                const int c = cc * 32 + lane;
-                const int r0 = max(0, cols - (tx + 1) * tw), r_end = cols - tx * tw;
-                if (c >= W || r0 >= r_end) continue;
-                unsigned* ht = hist + (tya[c] * 8 + tx) * 256;
+        // ------------------------------------------------------------ tile LUTs, one warp per tile, no block barrier inside
+        // (OpenCV CLAHE_CalcLut_Body).  A lane owns one P column of the tile (slice row a -> up to th
+        // lanes busy) and walks the tile's P rows eight at a time.  Background pixels (u == 0) are never counted: every
+        // padded tile holds th * tw pixels, so bin 0 is recovered by subtraction (and HE's bin 0 in its CDF).
+        unsigned* ht = reinterpret_cast<unsigned*>(R + warp * 1024);
+        const uint8_t* hub = reinterpret_cast<const uint8_t*>(ht);
+        const bool long_fold = ptmisc[0] != 0;
+        const int L0 = lutl[0], area = th * tw, clip = p.clip;
+        for (;;) {
+            int q = 0;
+            if (lane == 0) q = atomicAdd(&misc[22], 1);
+            q = __shfl_sync(FULL, q, 0);
+            if (q >= 64) break;
+            const int tile = kTileOrder[q], ty = tile >> 3, tx = tile & 7;
+            reinterpret_cast<uint4*>(ht)[lane] = make_uint4(0, 0, 0, 0);
+            reinterpret_cast<uint4*>(ht)[lane + 32] = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+            const int a_lo = ty * th, a_hi = a_lo + th;                      // slice rows of the tile (padded extent)
+            const int b_lo = tx * tw, b_hi = b_lo + tw;                      // slice columns of the tile (padded extent)
+            const int r0 = max(0, cols - b_hi), r_end = cols - b_lo;         // real P rows of the tile (empty if r0 >= r_end)
+            uint32_t seen = 0;
+            // real pixels
+            for (int a0 = a_lo; a0 < min(a_hi, rows); a0 += 32) {
+                const int c = a0 + lane;
+                if (c >= min(a_hi, rows)) continue;
                 const uint8_t* px = su + r0 * W + c;
                 int r = r0;
                 for (; r + 7 < r_end; r += 8, px += 8 * W) {       // eight independent loads in flight
                     uint32_t v[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = px[i * W];
-                    if ((v[0] | v[1] | v[2] | v[3] | v[4] | v[5] | v[6] | v[7]) == 0) continue;
+                    const uint32_t any = v[0] | v[1] | v[2] | v[3] | v[4] | v[5] | v[6] | v[7];
+                    if (any == 0) continue;
+                    seen |= any;
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
                         if (v[i]) atomicAdd(&ht[v[i]], 1u);
@@ -262,6 +345,7 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const __grid
                 for (; r + 3 < r_end; r += 4, px += 4 * W) {
                     const uint32_t v0 = px[0], v1 = px[W], v2 = px[2 * W], v3 = px[3 * W];    // loads first, atomics after
                     if ((v0 | v1 | v2 | v3) == 0) continue;
+                    seen |= v0 | v1 | v2 | v3;
                     if (v0) atomicAdd(&ht[v0], 1u);
                     if (v1) atomicAdd(&ht[v1], 1u);
                     if (v2) atomicAdd(&ht[v2], 1u);
@@ -269,33 +353,82 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const __grid
                 }
                 for (; r < r_end; ++r, px += W) {
                     const uint32_t v = px[0];
-                    if (v) atomicAdd(&ht[v], 1u);
+                    if (v) { atomicAdd(&ht[v], 1u); seen = 1; }
                 }
             }
-        }
-        __syncthreads();
-        // HE's histogram = sum of the 64 tile histograms (before the CLAHE padding is added)
-        if (want_he) {
-            // thread = one gray level and 1 / kParts of the tiles; partial sums meet in he_hist
-            constexpr int kParts = kThreads / 256;
-            const int part = tid >> 8, u = tid & 255;
-            unsigned acc = 0;
-            for (int t = part; t < 64; t += kParts) acc += hist[t * 256 + u];
-            if (acc) atomicAdd(&he_hist[u], acc);
-        }
-        __syncthreads();
-        // BORDER_REFLECT_101 padding (OpenCV pads bottom / right up to the 8x8 tile grid): the few padded pixels
-        const int prow = th * 8, pcol = tw * 8;
-        // region A: padded slice rows ap in [rows, prow), every padded column; region B: real rows, padded columns
-        for (int bp = tid; bp < pcol; bp += kThreads) {
-            const int b = reflect101(bp, cols), tcol = bp / tw, prow_off = (cols - 1 - b) * W;
-            for (int ap = rows; ap < prow; ++ap)
-                add_hist(hist + ((ap / th) * 8 + tcol) * 256, su[prow_off + reflect101(ap, rows)]);
-        }
-        for (int a = tid; a < rows; a += kThreads) {
-            const int trow = tya[a] * 8;
-            for (int bp = cols; bp < pcol; ++bp)
-                add_hist(hist + (trow + bp / tw) * 256, su[(cols - 1 - reflect101(bp, cols)) * W + a]);
+            bool nz = __any_sync(FULL, seen != 0);
+            __syncwarp();                                         // the warp's shared-memory atomics are ordered before the reads below
+            // HE's histogram = sum of the tile histograms of the REAL pixels (before the CLAHE padding is added)
+            if (want_he && nz) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const unsigned h = ht[lane + 32 * k];
+                    if (h) atomicAdd(&he_hist[lane + 32 * k], h);
+                }
+                __syncwarp();                                     // ... and those reads before the padding is added
+            }
+            // BORDER_REFLECT_101 padding (OpenCV pads bottom / right up to the 8x8 tile grid): padded slice rows a >= rows
+            // over every column of the tile, and real rows over the padded columns b >= cols
+            if (a_hi > rows || b_hi > cols) {
+                uint32_t seen2 = 0;
+                // padded slice rows (at most 8 of them): lanes run along the tile's slice columns b, padded ones included
+                for (int ap = max(a_lo, rows); ap < a_hi; ++ap) {
+                    const int asrc = reflect101(ap, rows);
+                    for (int b0 = b_lo; b0 < b_hi; b0 += 32) {
+                        const int b = b0 + lane;
+                        if (b >= b_hi) continue;
+                        const uint32_t v = su[(cols - 1 - (b < cols ? b : reflect101(b, cols))) * W + asrc];
+                        if (v) { atomicAdd(&ht[v], 1u); seen2 = 1; }
+                    }
+                }
+                // padded slice columns (at most 8) over the real rows: lanes run along the tile's slice rows a
+                for (int bp = max(b_lo, cols); bp < b_hi; ++bp) {
+                    const uint8_t* prow = su + (cols - 1 - reflect101(bp, cols)) * W;
+                    for (int a0 = a_lo; a0 < min(a_hi, rows); a0 += 32) {
+                        const int a = a0 + lane;
+                        if (a >= min(a_hi, rows)) continue;
+                        const uint32_t v = prow[a];
+                        if (v) { atomicAdd(&ht[v], 1u); seen2 = 1; }
+                    }
+                }
+                nz |= __any_sync(FULL, seen2 != 0);
+            }
+            __syncwarp();
+            if (!nz) {                                            // no brain in this tile: the plane's constant LUT
+                reinterpret_cast<uint2*>(Tc + tile * 256)[lane] = reinterpret_cast<const uint2*>(pt + kPTProto)[lane];
+                continue;
+            }
+            // fold the u-bins into L-bins, 8 L-bins per lane
+            int hb[8];
+            if (!long_fold) {
+                const uint4 f0 = reinterpret_cast<const uint4*>(fold)[lane * 2], f1 = reinterpret_cast<const uint4*>(fold)[lane * 2 + 1];
+                const uint32_t f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    hb[k] = (int)(*reinterpret_cast<const unsigned*>(hub + (f[k] & 0xffffu)) + *reinterpret_cast<const unsigned*>(hub + (f[k] >> 16)));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int Lb = lane * 8 + k;
+                    int acc = 0;
+                    for (int u = ustart[Lb]; u < (int)ustart[Lb + 1]; ++u) acc += (int)ht[u];
+                    hb[k] = acc;
+                }
+            }
+            {
+                // the tile's background pixels were never counted: th * tw minus everything else, into L-bin LUT_L[0]
+                int tot = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) tot += hb[k];
+                const int zeros = area - warp_sum(tot);
+                if (L0 == 0) { if (lane == 0) hb[0] += zeros; }
+                else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) if (lane * 8 + k == L0) hb[k] += zeros;
+                }
+            }
+            reinterpret_cast<uint2*>(Tc + tile * 256)[lane] = clip_cdf_tile(hb, lane, clip, p.lut_scale);
+            __syncwarp();                                         // the scratch histogram is cleared for the next tile
         }
     } else if (want_he) {
         // HE without CLAHE: plain 256-bin histogram, zero words skipped
@@ -317,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const __grid
 
     // ---------------------------------------------------------------- HE CDF -> LUT; packed HE | GC | LT table
     // Built by warps 0-7 (one gray level per thread).  With CLAHE on, the other warps do not wait for it: they start on
-    // the tile LUTs below, and the table is published by the barrier behind those.
+    // the pair tables below, and the table is published by the barrier behind those.
     auto build_t3 = [&](bool active, auto sync8) {           // active: tid < 256; sync8: a barrier over all callers
         // (with CLAHE on, he_hist[0] is still empty: the background count is npx minus everything else)
         int h = 0, c = 0;
@@ -353,8 +486,20 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const __grid
         uint32_t* o_gc = reinterpret_cast<uint32_t*>(p.out_gc ? p.out_gc + s * p.out_pitch : nullptr);
         uint32_t* o_lt = reinterpret_cast<uint32_t*>(p.out_lt ? p.out_lt + s * p.out_pitch : nullptr);
         const uint32_t z = t3[0];
-        for (int q = tid; q < nw; q += kThreads) {
-            const uint32_t w = su32[q];
+        const uint32_t z_he = (z & 0xffu) * 0x01010101u, z_gc = ((z >> 8) & 0xffu) * 0x01010101u, z_lt = ((z >> 16) & 0xffu) * 0x01010101u;
+        for (int q0 = warp * 32; q0 < nw; q0 += kThreads) {
+            const int q = q0 + lane;
+            const bool act = q < nw;
+            const uint32_t w = act ? su32[q] : 0u;
+            if (!__any_sync(FULL, w != 0)) {                     // 32 background words (two thirds of them): constants
+                if (act) {
+                    if (o_he) o_he[q] = z_he;
+                    if (o_gc) o_gc[q] = z_gc;
+                    if (o_lt) o_lt[q] = z_lt;
+                }
+                continue;
+            }
+            if (!act) continue;
             uint32_t a0 = z, a1 = z, a2 = z, a3 = z;
             if (w) { a0 = t3[w & 0xff]; a1 = t3[(w >> 8) & 0xff]; a2 = t3[(w >> 16) & 0xff]; a3 = t3[w >> 24]; }
             // transpose the 4 x 3 bytes: byte j of every a_k -> output word j
@@ -380,125 +525,18 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const __grid
     }
     if (want_lut && warp < 8) build_t3(true, [] { asm volatile("bar.sync 1, 256;" ::: "memory"); });
 
-    // ---------------------------------------------------------------- CLAHE: fold u-bins into L-bins, clip, CDF -> tile LUTs
-    // (OpenCV CLAHE_CalcLut_Body).  One warp per tile, 8 L-bins per lane.
-    const bool long_fold = misc[21] != 0;
-    const int L0 = lutl[0], area = th * tw, clip = p.clip;
-    // warps 0-7 come from the table above and take the last kLowTiles tiles, the other warps share the rest
-    constexpr int kLowTiles = kWarps >= 24 ? 16 : 24, kHighTiles = 64 - kLowTiles;
-    for (int t = warp >= 8 ? warp - 8 : kHighTiles + warp; t < (warp >= 8 ? kHighTiles : 64); t += (warp >= 8 ? kWarps - 8 : 8)) {
-        const unsigned* hu = hist + t * 256;
-        int hb[8];
-        if (!long_fold) {
-            const uint4 f0 = reinterpret_cast<const uint4*>(fold)[lane * 2], f1 = reinterpret_cast<const uint4*>(fold)[lane * 2 + 1];
-            const uint32_t f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-            const uint8_t* hub = reinterpret_cast<const uint8_t*>(hu);
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                hb[k] = (int)(*reinterpret_cast<const unsigned*>(hub + (f[k] & 0xffffu)) + *reinterpret_cast<const unsigned*>(hub + (f[k] >> 16)));
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int L = lane * 8 + k;
-                int acc = 0;
-                for (int u = ustart[L]; u < (int)ustart[L + 1]; ++u) acc += (int)hu[u];
-                hb[k] = acc;
-            }
-        }
-        {
-            // the tile's background pixels were never counted: th * tw minus everything else, into L-bin LUT_L[0]
-            int tot = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) tot += hb[k];
-            const int zeros = area - warp_sum(tot);
-            if (L0 == 0) { if (lane == 0) hb[0] += zeros; }
-            else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) if (lane * 8 + k == L0) hb[k] += zeros;
-            }
-        }
-        int clipped = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (hb[k] > clip) { clipped += hb[k] - clip; hb[k] = clip; }
-        clipped = warp_sum(clipped);
-        const int rb = clipped >> 8;
-        const int res = clipped & 255;
-        // residual: bins 0, step, 2*step, ... (res of them) get one more; walk this lane's 8 bins without dividing per bin
-        const int step = res > 0 ? small_div(256, res) : 256;
-        const int base = lane * 8;
-        int kn = small_div(base + step - 1, step);          // index of the first multiple of step that is >= base
-        int nxt = kn * step;
-        int run = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            hb[k] += rb;
-            const bool hit = (nxt == base + k) && (kn < res);
-            if (hit) { hb[k] += 1; nxt += step; ++kn; }
-            run += hb[k];
-            hb[k] = run;
-        }
-        const int excl = warp_incl_scan(run, lane) - run;
-        // saturate_cast<uchar>(cdf * lutScale): the product lies in [0, 255.0001], so int -> float and round-half-even both
-        // go through magic adds and the low byte of the sum is the result
-        uint32_t o[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float cdf = __fsub_rn(__uint_as_float(0x4b000000u + (uint32_t)(hb[k] + excl)), 8388608.0f);
-            o[k] = __float_as_uint(__fadd_rn(__fmul_rn(cdf, p.lut_scale), 12582912.0f));
-        }
-        const uint32_t lo = __byte_perm(__byte_perm(o[0], o[1], 0x0040), __byte_perm(o[2], o[3], 0x0040), 0x5410);
-        const uint32_t hi = __byte_perm(__byte_perm(o[4], o[5], 0x0040), __byte_perm(o[6], o[7], 0x0040), 0x5410);
-        reinterpret_cast<uint2*>(hist + t * 256)[lane] = make_uint2(lo, hi);      // T[t][L]: 256 bytes at the head of the tile's own slot
-    }
-    // interpolation tables (OpenCV CLAHE_Interpolation_Body): blend weight + table offsets per P row / P column.
-    //   P row r    (slice column b): weight xa, pair slot j = floor(txf) + 1 in [0, 8]  -> byte offset 2*j
-    //   P column c (slice row a)   : weight ya, tile rows ty1 / ty2
-    {
-        const float inv_tw = __fdiv_rn(1.0f, (float)tw), inv_th = __fdiv_rn(1.0f, (float)th);
-        for (int r = tid; r < cols; r += kThreads) {
-            const int b = cols - 1 - r;
-            const float txf = __fsub_rn(__fmul_rn((float)b, inv_tw), 0.5f);
-            const int t1 = (int)floorf(txf);
-            xw[r] = __fsub_rn(txf, (float)t1);
-            xo[r] = (uint32_t)(2 * (min(max(t1, -1), 7) + 1));
-        }
-        for (int a = tid; a < rows; a += kThreads) {
-            const float tyf = __fsub_rn(__fmul_rn((float)a, inv_th), 0.5f);
-            const int t1 = (int)floorf(tyf), t2 = t1 + 1;
-            yw[a] = __fsub_rn(tyf, (float)t1);
-            yo[a] = (uint32_t)max(t1, 0) | ((uint32_t)min(t2, 7) << 16);
-        }
-    }
-    __syncthreads();
-    if (want_lut) map_t3();                                  // HE | GC | LT outputs (the table was published by the barrier above)
     const bool use_tz = cols <= (kPairStride - kPairTy) / 4;
     // Pair tables: PT[ty][u][j] = (T[ty][tx1][LUT_L[u]], T[ty][tx2][LUT_L[u]]) as one 16-bit entry for the nine
     // horizontal neighbour pairs (tx1, tx2) = (0,0), (0,1), ..., (6,7), (7,7).  One 16-bit read fetches both operands
     // of a horizontal blend; a gray level's nine entries take 20 bytes (5 words: odd stride -> spread over the banks).
     // Thread = one gray level u and four tile rows: 8 byte reads (neighbouring u -> neighbouring L: conflict-free)
-    // and five 32-bit stores per tile row.
+    // and five 32-bit stores per tile row.  (The histogram scratch at the head of R is dead since the barrier above.)
     {
-        // (the tile LUTs move out of the way first: slots of 1 KB -> a compact [64][256] block behind the pair area)
-        uint8_t* Tc = R + kPairBytes;
-        uint2 tv[(64 * 32 + kThreads - 1) / kThreads];
-#pragma unroll
-        for (int j = 0; j < (64 * 32 + kThreads - 1) / kThreads; ++j) {
-            const int e = tid + j * kThreads;              // tile e / 32, 8-byte piece e % 32
-            if (e < 64 * 32) tv[j] = reinterpret_cast<const uint2*>(R + (e >> 5) * 1024)[e & 31];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < (64 * 32 + kThreads - 1) / kThreads; ++j) {
-            const int e = tid + j * kThreads;
-            if (e < 64 * 32) reinterpret_cast<uint2*>(Tc + (e >> 5) * 256)[e & 31] = tv[j];
-        }
-        __syncthreads();
-        const int uv = tid & 255, L = lutl[uv];
+        const int uv = tid & 255, Lv = lutl[uv];
         for (int ty = tid >> 8; ty < 8; ty += kThreads / 256) {
             uint32_t t[8];
 #pragma unroll
-            for (int tx = 0; tx < 8; ++tx) t[tx] = Tc[(ty * 8 + tx) * 256 + L];
+            for (int tx = 0; tx < 8; ++tx) t[tx] = Tc[(ty * 8 + tx) * 256 + Lv];
             uint32_t* dst = reinterpret_cast<uint32_t*>(R + ty * kPairStride + uv * 20);
             // pairs j = 0..8: (t0,t0) (t0,t1) (t1,t2) ... (t6,t7) (t7,t7), two 16-bit pairs per word
             dst[0] = (t[0] | (t[0] << 8)) | ((t[0] | (t[1] << 8)) << 16);
@@ -524,6 +562,7 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const __grid
         }
     }
     __syncthreads();
+    if (want_lut) map_t3();                                  // HE | GC | LT outputs (the table was published by the barrier above)
 
     // ---------------------------------------------------------------- CLAHE: bilinear blend + LUT_OUT
     // A warp owns 32 consecutive P columns (slice rows) over a band of P rows: the vertical weight / offsets stay in
@@ -599,12 +638,26 @@ __global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const __grid
     }
 }
 
+template <bool DO_CLAHE>
+__global__ void __launch_bounds__(kThreads, 2) enhance_dense_kernel(const __grid_constant__ DenseLaunch L) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int plane_k = (int)blockIdx.x >= L.first[2] ? 2 : ((int)blockIdx.x >= L.first[1] ? 1 : 0);
+    const DenseParams& p = L.plane[plane_k];
+    const size_t s = (size_t)((int)blockIdx.x - L.first[plane_k]);
+    if (p.rows == 182) dense_slice<DO_CLAHE, 182>(p, s, smem);
+    else if (p.rows == 218) dense_slice<DO_CLAHE, 218>(p, s, smem);
+    else dense_slice<DO_CLAHE, 0>(p, s, smem);
+}
+
 }  // namespace
 
 size_t dense_u_pitch(int npx) { return ((size_t)npx + 15) & ~(size_t)15; }
 
+// bytes of one plane's table block (dense_tables_kernel), a multiple of 16
+size_t dense_tabs_bytes(int rows, int cols) { return ((size_t)kPTW + (size_t)(rows + cols) * 8 + 15) & ~(size_t)15; }
+
 size_t dense_smem_bytes(int rows, int cols, bool clahe) {
-    return (size_t)kOffTabs + (clahe ? (size_t)(rows + cols) * 8 + kRBytes : 0) + 16 + dense_u_pitch(rows * cols);
+    return (size_t)kOffPT + (clahe ? dense_tabs_bytes(rows, cols) + kRBytes : 0) + dense_u_pitch(rows * cols);
 }
 
 bool dense_supported(int rows, int cols, bool clahe) {
@@ -613,12 +666,13 @@ bool dense_supported(int rows, int cols, bool clahe) {
            dense_smem_bytes(rows, cols, clahe) <= 227 * 1024;
 }
 
-int launch_enhance_dense_multi(const DensePlane* planes, int nplanes, const uint8_t* tables, cudaStream_t stream) {
+int launch_enhance_dense_multi(const DensePlane* planes, int nplanes, const uint8_t* tables, void* tabs_ws, size_t tabs_ws_bytes,
+                               cudaStream_t stream) {
     DenseLaunch L;
     memset(&L, 0, sizeof(L));
     int n = 0, total = 0;
     bool cl = false;
-    size_t smem = 0;
+    size_t smem = 0, tabs_used = 0;
     for (int i = 0; i < nplanes; ++i) {
         const DensePlane& q = planes[i];
         if (q.nslices <= 0 || (!q.out_he && !q.out_clahe && !q.out_gc && !q.out_lt)) continue;
@@ -638,13 +692,26 @@ int launch_enhance_dense_multi(const DensePlane* planes, int nplanes, const uint
         p.U = q.U; p.u_pitch = q.u_pitch; p.out_he = q.out_he; p.out_clahe = q.out_clahe; p.out_gc = q.out_gc; p.out_lt = q.out_lt;
         p.out_pitch = (size_t)q.rows * q.cols; p.tables = tables;
         p.rows = q.rows; p.cols = q.cols; p.th = q.th; p.tw = q.tw; p.clip = q.clip; p.lut_scale = q.lut_scale;
-        p.magic_w = (unsigned)(0x100000000ull / (unsigned)q.rows) + 1u;
+        if (cl) {
+            const size_t tb = dense_tabs_bytes(q.rows, q.cols);
+            if (!tabs_ws || (reinterpret_cast<uintptr_t>(tabs_ws) & 15) || tabs_used + tb > tabs_ws_bytes) {
+                set_error("enhance_dense: table workspace of %zu bytes (16-byte aligned) needed, %zu given", tabs_used + tb, tabs_ws_bytes);
+                return MSL_ERR_WORKSPACE;
+            }
+            p.ptabs = static_cast<const uint8_t*>(tabs_ws) + tabs_used;
+            tabs_used += tb;
+        }
         L.first[n] = total;
         total += q.nslices;
         ++n;
     }
     if (n == 0) return MSL_OK;
     for (int i = n; i < 4; ++i) L.first[i] = total;        // unused stacks start behind the grid
+    if (cl) {
+        ProfScope prof(K_ENH_DENSE_TABLES, stream);
+        dense_tables_kernel<<<n, 288, 0, stream>>>(L);
+        MSL_LAUNCH_CHECK("dense_tables_kernel");
+    }
     ProfScope prof(K_ENH_DENSE, stream);
     if (cl) {
         MSL_CUDA_CHECK(cudaFuncSetAttribute(enhance_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -655,16 +722,6 @@ int launch_enhance_dense_multi(const DensePlane* planes, int nplanes, const uint
     }
     MSL_LAUNCH_CHECK("enhance_dense_kernel");
     return MSL_OK;
-}
-
-int launch_enhance_dense(const uint8_t* U, size_t u_pitch, int nslices, int rows, int cols,
-                         uint8_t* out_he, uint8_t* out_clahe, uint8_t* out_gc, uint8_t* out_lt, const uint8_t* tables,
-                         int th, int tw, int clip, float lut_scale, cudaStream_t stream) {
-    DensePlane q;
-    q.U = U; q.u_pitch = u_pitch; q.nslices = nslices; q.rows = rows; q.cols = cols;
-    q.out_he = out_he; q.out_clahe = out_clahe; q.out_gc = out_gc; q.out_lt = out_lt;
-    q.th = th; q.tw = tw; q.clip = clip; q.lut_scale = lut_scale;
-    return launch_enhance_dense_multi(&q, 1, tables, stream);
 }
 
 }  // namespace msl

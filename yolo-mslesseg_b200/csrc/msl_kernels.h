@@ -26,7 +26,8 @@ enum KernelKind {
     K_BGR2GRAY = 22,
     K_PNG_PACK = 23,
     K_NONZERO_FLAGS = 24,
-    K_NKIND = 25
+    K_ENH_DENSE_TABLES = 25,   // per-launch plane tables of enhance_dense
+    K_NKIND = 26
 };
 
 // RAII: counts the launch and, when profiling is enabled, brackets it with CUDA events on `stream`.
@@ -95,10 +96,10 @@ struct DensePlane {
     int th, tw, clip; float lut_scale;                // CLAHE geometry of a rows x cols slice
 };
 // up to three stacks in ONE launch (they must agree on whether CLAHE is wanted)
-int launch_enhance_dense_multi(const DensePlane* planes, int nplanes, const uint8_t* tables, cudaStream_t stream);
-int launch_enhance_dense(const uint8_t* U, size_t u_pitch, int nslices, int rows, int cols,
-                         uint8_t* out_he, uint8_t* out_clahe, uint8_t* out_gc, uint8_t* out_lt, const uint8_t* tables,
-                         int th, int tw, int clip, float lut_scale, cudaStream_t stream);
+// tabs_ws: device scratch for the per-plane tables, sum of dense_tabs_bytes(rows, cols) over the CLAHE stacks, 16-byte aligned
+size_t dense_tabs_bytes(int rows, int cols);
+int launch_enhance_dense_multi(const DensePlane* planes, int nplanes, const uint8_t* tables, void* tabs_ws, size_t tabs_ws_bytes,
+                               cudaStream_t stream);
 
 // R1-R2
 int launch_recon(const uint8_t* slices, size_t slice_pitch, const int32_t* vol_of_slice, const int32_t* idx_of_slice,

@@ -22,7 +22,7 @@ const char* const kNames[K_NKIND] = {
     "enhance_slices_u8_none", "enhance_slices_u8_he", "enhance_slices_u8_clahe", "enhance_slices_u8_gc", "enhance_slices_u8_lt",
     "init_stats", "plane_stats_f32", "lesion_flags", "norm_scatter",
     "recon_fill", "recon_slot_map", "recon_gather", "consensus_eval", "confusion_counts", "enhance_dense",
-    "combine_predictions", "slice_counts", "bgr_to_gray", "png_pack", "nonzero_flags",
+    "combine_predictions", "slice_counts", "bgr_to_gray", "png_pack", "nonzero_flags", "enhance_dense_tables",
 };
 }  // namespace
 
