@@ -2,7 +2,7 @@
 """bench.py - throughput of the YOLO-MSLesSeg voxel path on B200 (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (port), host cores
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path (oracle/_ref), host cores
 
 One STEP = one pass of the hot path over one batch of synthetic patients resident in HBM:
   enhance->slice : lesion-slice flags (E0) + HE / CLAHE / GC / LT x axial / coronal / sagital over ALL
@@ -148,7 +148,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32+u8 (f64 metrics)", "data": "synthetic",
         "config": workload_config(args, {"note": "each step is a bounded sample of the workload: "
                                          f"{npat} patients through the reference's CPU path"}),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": CB.KIND, "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -391,7 +391,7 @@ def run_ours(args):
         with CB.CpuBaseline(CB.default_sample_patients(cores), cores, num_cortes=args.num_cortes) as cb:
             cb.step()
             sec = cb.step()
-            cpu = {"value": cb.voxels_per_step / sec / 1e9, "unit": UNIT, "cores": cores, "kind": "port", "sample": cb.describe()}
+            cpu = {"value": cb.voxels_per_step / sec / 1e9, "unit": UNIT, "cores": cores, "kind": CB.KIND, "sample": cb.describe()}
 
     if rank == 0:
         line = {

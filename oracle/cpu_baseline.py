@@ -1,7 +1,8 @@
 """CPU baseline runner.  BENCH INFRASTRUCTURE - NOT PRODUCT CODE.
 
-Times the reference's CPU path (oracle/ref_path.py: the same cv2 / NumPy / scikit-learn calls the
-reference makes) on the host cores of the box bench.py runs on, over a bounded sample of the bench
+Times the reference's CPU path - the REAL reference functions through oracle/ref_real.py when the package is staged
+under oracle/_ref (oracle/build_ref.py; kind "reference"), else the port oracle/ref_path.py (the same cv2 / NumPy /
+scikit-learn calls; kind "port") - on the host cores of the box bench.py runs on, over a bounded sample of the bench
 workload: whole synthetic patients, every enhancement x plane over ALL slices, recon of the three
 planes, consensus, metrics of the three planes + consensus.
 
@@ -26,7 +27,12 @@ for _p in (str(ROOT), str(ROOT / "yolo-mslesseg_b200")):
         sys.path.insert(0, _p)
 
 from oracle import oracle as O            # noqa: E402
-from oracle import ref_path as R          # noqa: E402
+from oracle import ref_real as _RR         # noqa: E402
+if _RR.available():
+    R, KIND = _RR, "reference"
+else:                                     # pragma: no cover - only without oracle/_ref
+    from oracle import ref_path as R      # noqa: E402
+    KIND = "port"
 from mslesseg_b200 import synthetic as S  # noqa: E402
 
 _PATIENTS = []          # filled in the parent before the pool forks
@@ -85,6 +91,8 @@ class CpuBaseline:
         self.n_patients = n_patients
         global _PATIENTS
         _PATIENTS = [S.make_patient(n + 1, config_id=config_id, num_cortes=num_cortes) for n in range(n_patients)]
+        if KIND == "reference":
+            _RR._ns()                      # import the reference once in the parent; the forked workers inherit it
         self.pool = mp.get_context("fork").Pool(self.cores)
         self.voxels_per_step = n_patients * int(np.prod(S.SHAPE_XYZ))
 
