@@ -149,6 +149,62 @@ size_t msl_png_bytes(int H, int W, int channels);
 int msl_png_pack(const uint8_t* pixels, int n, int H, int W, int channels,
                  uint8_t* out, size_t out_pitch_bytes, msl_stream_t stream);
 
+/* ---- byte-stream codec, encode side: deflate on the device -----------------------
+ * Replaces the zlib work behind plt.imsave (scripts/extraer_dataset.py:192,197), cv2.imwrite (utils/utils.py:393,
+ * scripts/generar_predicciones.py:153) and nib.save (utils/utils.py:176-177): what crosses PCIe and lands on disk are the
+ * compressed files.  Every stream is one fixed-Huffman deflate block (RFC 1951) with run matches at distance 1 and at an
+ * optional second distance `dist2` (<= 16; 4 suits RGBA pixels and float32 voxels), inside the container asked for:
+ *   MSL_Z_RAW   bare deflate            MSL_Z_ZLIB  RFC 1950 (0x78 0x01, Adler-32)
+ *   MSL_Z_GZIP  RFC 1952 member; header carries an FEXTRA subfield 'M','S' = {u32 member bytes, u32 raw bytes}, so a
+ *               file that is a sequence of such members can be split without decoding (msl_inflate runs them in parallel)
+ *   MSL_Z_PNG   a complete PNG file (signature, IHDR, one IDAT, IEND), filter type 0 on every scanline
+ * The n streams are written back to back: stream i occupies out[out_off[i], out_off[i+1]) (out_off: DEVICE uint64
+ * [n + 1]); out_off[n] > out_cap means the capacity was too small (nothing past it was written).
+ * msl_deflate_bound() is a capacity that always suffices.  out_meta (optional, DEVICE uint32 [n][4]) receives per stream
+ * {container bytes, raw bytes, Adler-32 / CRC-32 of the raw bytes, 0}.  ws: msl_deflate_workspace_bytes(...), 16-byte aligned.
+ *
+ * msl_deflate_chunks: `total_len` bytes at src cut into n = ceil(total_len / chunk_len) streams (chunk_len < 16 MB).
+ * msl_png_encode    : pixels uint8 [n][H][W][channels] (channels 1, 2, 3 or 4) -> n PNG files. */
+#define MSL_Z_RAW  0
+#define MSL_Z_ZLIB 1
+#define MSL_Z_GZIP 2
+#define MSL_Z_PNG  3
+size_t msl_deflate_bound(int n, int container, size_t raw_len_per_stream);
+size_t msl_deflate_workspace_bytes(int n, int container, size_t raw_len_per_stream);
+int msl_deflate_chunks(const uint8_t* src, size_t total_len, size_t chunk_len, int container, int dist2,
+                       uint8_t* out, size_t out_cap, uint64_t* out_off, uint32_t* out_meta,
+                       void* ws, size_t ws_bytes, msl_stream_t stream);
+int msl_png_encode(const uint8_t* pixels, int n, int H, int W, int channels,
+                   uint8_t* out, size_t out_cap, uint64_t* out_off,
+                   void* ws, size_t ws_bytes, msl_stream_t stream);
+
+/* ---- byte-stream codec, decode side: inflate on the device -----------------------
+ * Replaces the zlib work behind nib.load(...).get_fdata() (utils/Paciente.py:168,179, utils/utils.py:156), Image.open
+ * (scripts/reconstruir_volumen.py:141) and cv2.imread (utils/utils.py:391): the host uploads FILE bytes.
+ * msl_inflate: n independent streams, ONE WARP each (stored, fixed and dynamic Huffman blocks; any conforming deflate
+ * stream).  Stream i = src[src_off[i], src_off[i+1]) in container MSL_Z_RAW / MSL_Z_ZLIB / MSL_Z_GZIP (a gzip stream may
+ * hold several members, decoded one after the other); its output goes to dst[dst_off[i], dst_off[i+1]) (the capacity).
+ * src must be 4-byte aligned; src_off / dst_off are DEVICE uint64 [n + 1].  status: DEVICE uint32 [n][4] =
+ * {0 or an error code (1 header, 2 block, 3 code, 4 distance, 5 out of space, 6 input ended), bytes produced, the
+ * Adler-32 / CRC-32 stored in the (last) trailer, the stored ISIZE (gzip)}.  Parallelism = number of streams: a file
+ * written by msl_deflate_chunks(MSL_Z_GZIP) splits into its members (the 'MS' subfield gives their sizes).
+ *
+ * msl_png_unfilter: undoes the PNG scanline filters (types 0-4) of n inflated images of H x W pixels, bytes_per_pixel
+ * in {1, 2, 3, 4} (8-bit gray, gray+alpha, RGB, RGBA; not interlaced), image i at raw[raw_off[i], raw_off[i+1]), in place,
+ * and writes the FIRST channel to out [n][H][W] - what cargar_y_preprocesar_imagen keeps (scripts/reconstruir_volumen.py:
+ * 141-145) and msl_recon consumes.  status: DEVICE uint32 [n], 0 = ok.
+ *
+ * msl_nifti_convert: nvox voxels of NIfTI datatype code `datatype` (2 uint8, 4 int16, 8 int32, 16 float32, 64 float64,
+ * 256 int8, 512 uint16, 768 uint32; little endian, any alignment), scaled by slope / inter when scaled != 0 (get_fdata
+ * semantics, float64 arithmetic), to out_f32 and / or out_u8 (either may be NULL).  *inexact (DEVICE uint64) counts the
+ * values an output could not hold exactly. */
+int msl_inflate(const uint8_t* src, size_t src_bytes, const uint64_t* src_off, int n, int container,
+                uint8_t* dst, const uint64_t* dst_off, uint32_t* status, msl_stream_t stream);
+int msl_png_unfilter(uint8_t* raw, const uint64_t* raw_off, int n, int H, int W, int bytes_per_pixel,
+                     uint8_t* out, uint32_t* status, msl_stream_t stream);
+int msl_nifti_convert(const uint8_t* payload, int datatype, uint64_t nvox, double slope, double inter, int scaled,
+                      float* out_f32, uint8_t* out_u8, uint64_t* inexact, msl_stream_t stream);
+
 /* ---- host hand-off helpers: copy only the non-zero box of a result ------------------------------
  * Skull-stripped volumes are two thirds background and predicted masks ~99 % zeros, and the device-to-host copy of the
  * results is what bounds the path end to end.  msl_nonzero_flags marks which slices (a) and rows (b) of a uint8 stack

@@ -1,0 +1,222 @@
+"""GPU: the device byte-stream codec (msl_codec.cu / msl_inflate.cu) against zlib, gzip and Pillow on the host."""
+import gzip
+import io
+import zlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(cuda_device):
+    from mslesseg_b200 import _lib, ops
+    _lib.load()
+    return ops
+
+
+def _payloads():
+    rng = np.random.default_rng(5)
+    out = {}
+    out["zeros"] = np.zeros(200_000, np.uint8)
+    out["noise"] = rng.integers(0, 256, 70_001, dtype=np.uint8)
+    mixed = np.zeros(300_000, np.uint8)
+    mixed[50_000:90_000] = rng.integers(0, 256, 40_000, dtype=np.uint8)
+    mixed[150_000:150_700] = 7
+    mixed[200_000:260_000:3] = 255
+    out["mixed"] = mixed
+    f = np.zeros(60_000, np.float32)
+    f[10_000:40_000] = np.round(rng.uniform(1, 1500, 30_000))
+    out["float32"] = f.view(np.uint8)
+    out["tiny"] = np.array([1, 2, 3], np.uint8)
+    out["one_run"] = np.full(65_536 * 2 + 5, 9, np.uint8)
+    out["empty"] = np.zeros(0, np.uint8)
+    return out
+
+
+@pytest.mark.parametrize("container", ["raw", "zlib", "gzip"])
+def test_deflate_chunks_decode_with_zlib(ops, cuda_device, container):
+    import torch
+    for name, data in _payloads().items():
+        for chunk, d2 in ((65536, 0), (65536, 4), (20_000, 4), (1 << 20, 0)):
+            src = torch.from_numpy(data.copy()).to(cuda_device)
+            ps = ops.deflate_chunks(src, chunk_len=chunk, container=container, dist2=d2)
+            packed, off = ps.to_host()
+            meta = ps.meta.cpu().numpy().astype(np.int64) & 0xffffffff
+            n = len(off) - 1
+            assert n == max(1, -(-data.size // chunk))
+            got = []
+            for i in range(n):
+                b = packed[off[i]:off[i + 1]].tobytes()
+                assert meta[i, 0] == len(b)
+                if container == "raw":
+                    got.append(zlib.decompress(b, wbits=-15))
+                elif container == "zlib":
+                    got.append(zlib.decompress(b))
+                    assert meta[i, 2] == zlib.adler32(got[-1])
+                else:
+                    got.append(gzip.decompress(b))
+                    assert meta[i, 2] == zlib.crc32(got[-1])
+                    assert b[12:14] == b"MS" and int.from_bytes(b[16:20], "little") == len(b) and int.from_bytes(b[20:24], "little") == len(got[-1])
+                assert meta[i, 1] == len(got[-1])
+            assert b"".join(got) == data.tobytes(), (name, chunk, d2)
+            if container == "gzip":          # the members back to back are one valid .gz file
+                assert gzip.decompress(packed[:off[-1]].tobytes()) == data.tobytes()
+            if name in ("zeros", "one_run") and data.size > 100_000:
+                assert off[-1] < data.size // 50, (name, off[-1])
+            if name == "noise":
+                assert off[-1] < data.size * 1.07 + 64 * n
+
+
+def test_png_encode_decodes_with_pillow(ops, cuda_device):
+    import torch
+    from PIL import Image
+    rng = np.random.default_rng(9)
+    for shape in ((5, 218, 182), (3, 182, 218, 4), (2, 37, 53, 3), (2, 16, 20, 2), (1, 1, 1), (4, 182, 182, 4)):
+        px = np.zeros(shape, np.uint8)
+        if px.ndim == 3:
+            px[:, 5:-5, 7:-7] = rng.integers(0, 256, px[:, 5:-5, 7:-7].shape, dtype=np.uint8) if shape[1] > 10 else 200
+            px[0] = 0
+        else:
+            g = np.zeros(shape[:3], np.uint8)
+            g[:, 3:-3, 4:-4] = rng.integers(0, 256, g[:, 3:-3, 4:-4].shape, dtype=np.uint8)
+            px[..., :] = g[..., None]
+            if shape[3] in (2, 4):
+                px[..., -1] = 255
+        files = ops.png_encode(torch.from_numpy(px).to(cuda_device)).files()
+        assert len(files) == shape[0]
+        for i, f in enumerate(files):
+            im = Image.open(io.BytesIO(f))
+            im.load()
+            a = np.array(im)
+            assert im.mode == {3: "L", 4: {4: "RGBA", 3: "RGB", 2: "LA"}.get(shape[-1])}[px.ndim] if px.ndim == 4 else im.mode == "L"
+            assert np.array_equal(a, px[i]), (shape, i)
+        stored = sum(len(f) for f in files)
+        assert stored < px.size * 1.08 + 200 * shape[0]
+    # a blank stack compresses to almost nothing; cv2 reads the files too
+    cv2 = pytest.importorskip("cv2")
+    blank = torch.zeros((3, 218, 182), dtype=torch.uint8, device=cuda_device)
+    files = ops.png_encode(blank).files()
+    assert all(len(f) < 600 for f in files)
+    assert np.array_equal(cv2.imdecode(np.frombuffer(files[0], np.uint8), cv2.IMREAD_UNCHANGED), np.zeros((218, 182), np.uint8))
+
+
+@pytest.fixture(scope="module")
+def codec(ops):
+    from mslesseg_b200 import codec
+    return codec
+
+
+def test_inflate_decodes_zlib_gzip_and_own_streams(ops, codec, cuda_device):
+    import torch
+    pl = _payloads()
+    # streams written by zlib at several levels (dynamic, fixed and stored blocks), containers raw / zlib / gzip
+    for container, wbits in (("raw", -15), ("zlib", 15), ("gzip", 31)):
+        pieces, sizes, want = [], [], []
+        for name, data in pl.items():
+            for level in (0, 1, 6, 9):
+                c = zlib.compressobj(level, zlib.DEFLATED, wbits)
+                pieces.append(c.compress(data.tobytes()) + c.flush())
+                sizes.append(data.size)
+                want.append(data)
+            c = zlib.compressobj(6, zlib.DEFLATED, wbits, 9, zlib.Z_FIXED)
+            pieces.append(c.compress(data.tobytes()) + c.flush())
+            sizes.append(data.size)
+            want.append(data)
+        out, off = codec.inflate(pieces, sizes, container, cuda_device)
+        host = out.cpu().numpy()
+        for i, w in enumerate(want):
+            assert np.array_equal(host[off[i]:off[i] + w.size], w), (container, i)
+    # multi-member gzip as ONE stream (a foreign file: `cat a.gz b.gz`), and our own members one warp each
+    a, b = pl["mixed"], pl["noise"]
+    cat = gzip.compress(a.tobytes(), 6) + gzip.compress(b.tobytes(), 1)
+    out, off = codec.inflate([cat], [a.size + b.size], "gzip", cuda_device)
+    assert np.array_equal(out.cpu().numpy()[:a.size + b.size], np.concatenate([a, b]))
+    ps = ops.deflate_chunks(torch.from_numpy(pl["float32"].copy()).to(cuda_device), chunk_len=65536, container="gzip", dist2=4)
+    data, o = ps.to_host()
+    blob = data[:o[-1]].tobytes()
+    members = codec.gzip_members(blob)
+    assert members is not None and len(members) == len(o) - 1
+    out, off = codec.inflate([blob[p:p + m] for p, m, _ in members], [r for _, _, r in members], "gzip", cuda_device)
+    got = np.concatenate([out.cpu().numpy()[off[i]:off[i] + members[i][2]] for i in range(len(members))])
+    assert np.array_equal(got, pl["float32"])
+    # damaged input is reported, not decoded
+    bad = bytearray(zlib.compress(pl["mixed"].tobytes(), 6))
+    bad[40] ^= 0x55
+    with pytest.raises(codec.CodecError):
+        codec.inflate([bytes(bad)], [pl["mixed"].size], "zlib", cuda_device)
+    with pytest.raises(codec.CodecError):
+        codec.inflate([zlib.compress(pl["noise"].tobytes())], [100], "zlib", cuda_device)      # output region too small
+
+
+def test_png_decode_first_channel(ops, codec, cuda_device):
+    import torch
+    from PIL import Image
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(12)
+    masks = (rng.random((6, 182, 218)) > 0.97).astype(np.uint8) * 255
+    masks[0] = 0
+    files = []
+    for i, m in enumerate(masks):       # cv2.imwrite like guardar_prediccion (scripts/generar_predicciones.py:153)
+        ok, buf = cv2.imencode(".png", m, [cv2.IMWRITE_PNG_COMPRESSION, 3])
+        files.append(buf.tobytes())
+    got = codec.png_decode_first_channel(files, cuda_device).cpu().numpy()
+    assert np.array_equal(got, masks)
+    # Pillow with its adaptive filters, gray / RGB / RGBA / LA, smooth content so that every filter type shows up
+    yy, xx = np.mgrid[0:97, 0:131]
+    for mode, bpp in (("L", 1), ("RGB", 3), ("RGBA", 4), ("LA", 2)):
+        imgs, files = [], []
+        for k in range(4):
+            base = ((np.sin(xx / (7.0 + k)) + np.cos(yy / (5.0 + k))) * 60 + 128 + rng.integers(0, 3 + 20 * k, xx.shape)).clip(0, 255).astype(np.uint8)
+            arr = base if bpp == 1 else np.stack([np.roll(base, c * 3, axis=1) for c in range(bpp)], axis=-1)
+            bio = io.BytesIO()
+            Image.fromarray(arr, mode).save(bio, format="PNG", compress_level=k + 1)
+            files.append(bio.getvalue())
+            imgs.append(arr if bpp == 1 else arr[..., 0])
+        got = codec.png_decode_first_channel(files, cuda_device).cpu().numpy()
+        assert np.array_equal(got, np.stack(imgs)), mode
+    # our own encoder's files
+    px = torch.from_numpy(masks).to(cuda_device)
+    assert np.array_equal(codec.png_decode_first_channel(ops.png_encode(px).files(), cuda_device).cpu().numpy(), masks)
+    with pytest.raises(codec.CodecError):
+        bio = io.BytesIO()
+        Image.fromarray(masks[1]).convert("P").save(bio, format="PNG")
+        codec.png_decode_first_channel([bio.getvalue()], cuda_device)
+
+
+def test_nifti_gz_round_trip_on_device(ops, codec, cuda_device, tmp_path):
+    import torch
+    from mslesseg_b200 import nifti, synthetic as S
+    pat = S.make_patient(2, config_id=1, num_cortes=10)
+    aff = np.array([[1.0, 0, 0, -90], [0, 1.0, 0, -126], [0, 0, 1.0, -72], [0, 0, 0, 1.0]])
+    # a file written by the host writer with Python's gzip (one member, dynamic Huffman) -> device reader
+    p1 = tmp_path / "P2_T1_FLAIR.nii.gz"
+    nifti.save(S.as_xyz(pat.flair), aff, p1)
+    vol, shape, affine = codec.nifti_load_device(p1, cuda_device, torch.float32)
+    assert shape == (182, 218, 182) and np.allclose(affine, aff)
+    assert np.array_equal(vol.cpu().numpy(), pat.flair)
+    p2 = tmp_path / "P2_MASK.nii.gz"
+    nifti.save(S.as_xyz(pat.gt).astype(np.float32), aff, p2)
+    m, _, _ = codec.nifti_load_device(p2, cuda_device, torch.uint8)
+    assert np.array_equal(m.cpu().numpy(), pat.gt)
+    # device writer -> Python's gzip / host reader, and back through the parallel member path
+    p3 = tmp_path / "out" / "P2_axial.nii.gz"
+    size = codec.nifti_save_device(vol, aff, p3)
+    assert size == p3.stat().st_size and size < pat.flair.nbytes // 2
+    arr, aff2 = nifti.load(p3)
+    assert arr.dtype == np.float32 and np.array_equal(S.as_zyx(arr) if hasattr(S, "as_zyx") else arr.transpose(2, 1, 0), pat.flair) and np.allclose(aff2, aff)
+    raw = gzip.decompress(p3.read_bytes())
+    assert len(raw) == 352 + pat.flair.nbytes
+    assert codec.gzip_members(p3.read_bytes()) is not None
+    vol2, _, _ = codec.nifti_load_device(p3, cuda_device, torch.float32)
+    assert torch.equal(vol2, vol)
+    p4 = tmp_path / "P2_consenso.nii.gz"
+    codec.nifti_save_device(m, aff, p4)
+    assert p4.stat().st_size < 100_000
+    arr, _ = nifti.load(p4)
+    assert arr.dtype == np.uint8 and np.array_equal(arr.transpose(2, 1, 0), pat.gt)
+    assert codec.nifti_read_header(p4)[0] == (182, 218, 182)
+    # values a uint8 volume cannot hold are refused
+    with pytest.raises(codec.CodecError):
+        codec.nifti_load_device(p1, cuda_device, torch.uint8)

@@ -293,6 +293,72 @@ int msl_png_pack(const uint8_t* pixels, int n, int H, int W, int channels, uint8
     return launch_png_pack(pixels, n, H, W, channels, out, out_pitch_bytes, (cudaStream_t)stream);
 }
 
+size_t msl_deflate_bound(int n, int container, size_t raw) {
+    if (n <= 0 || container < MSL_Z_RAW || container > MSL_Z_PNG) return 0;
+    return (size_t)n * deflate_slot_bytes(container, raw);
+}
+
+size_t msl_deflate_workspace_bytes(int n, int container, size_t raw) {
+    if (n <= 0 || container < MSL_Z_RAW || container > MSL_Z_PNG) return 0;
+    return deflate_workspace_bytes(n, container, raw);
+}
+
+int msl_deflate_chunks(const uint8_t* src, size_t total_len, size_t chunk_len, int container, int dist2, uint8_t* out, size_t out_cap,
+                       uint64_t* out_off, uint32_t* out_meta, void* ws, size_t ws_bytes, msl_stream_t stream) {
+    MSL_REQUIRE(container >= MSL_Z_RAW && container <= MSL_Z_GZIP, "container %d no válido (MSL_Z_RAW / ZLIB / GZIP)", container);
+    MSL_REQUIRE(chunk_len > 0, "chunk_len must be positive");
+    MSL_REQUIRE(out && out_off, "NULL out / out_off");
+    MSL_REQUIRE(src || total_len == 0, "NULL src");
+    const size_t n = total_len == 0 ? 1 : (total_len + chunk_len - 1) / chunk_len;
+    MSL_REQUIRE(n <= 0x7fffffff, "too many chunks");
+    return launch_deflate_pack(src, (int)n, chunk_len, chunk_len, total_len, 0, 0, 0, 0, container, dist2, out, out_cap,
+                               reinterpret_cast<unsigned long long*>(out_off), out_meta, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int msl_png_encode(const uint8_t* pixels, int n, int H, int W, int channels, uint8_t* out, size_t out_cap, uint64_t* out_off,
+                   void* ws, size_t ws_bytes, msl_stream_t stream) {
+    MSL_REQUIRE(n >= 0 && H > 0 && W > 0, "non-positive size");
+    MSL_REQUIRE(channels >= 1 && channels <= 4, "channels %d no válido (1..4)", channels);
+    MSL_REQUIRE(out_off, "NULL out_off");
+    if (n == 0) return MSL_OK;
+    MSL_REQUIRE(pixels && out, "NULL pointer");
+    const size_t rb = (size_t)W * channels;
+    MSL_REQUIRE(rb < (1u << 24), "scanline too long");
+    return launch_deflate_pack(pixels, n, (size_t)H * rb, 0, 0, H, (int)rb, W, channels, MSL_Z_PNG, channels > 1 ? channels : 0, out, out_cap,
+                               reinterpret_cast<unsigned long long*>(out_off), nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int msl_inflate(const uint8_t* src, size_t src_bytes, const uint64_t* src_off, int n, int container, uint8_t* dst, const uint64_t* dst_off,
+                uint32_t* status, msl_stream_t stream) {
+    MSL_REQUIRE(n >= 0, "negative stream count");
+    if (n == 0) return MSL_OK;
+    MSL_REQUIRE(src && src_off && dst && dst_off && status, "NULL pointer");
+    MSL_REQUIRE(container >= MSL_Z_RAW && container <= MSL_Z_GZIP, "container %d no válido (MSL_Z_RAW / ZLIB / GZIP)", container);
+    return launch_inflate(src, src_bytes, reinterpret_cast<const unsigned long long*>(src_off), n, container, dst,
+                          reinterpret_cast<const unsigned long long*>(dst_off), status, (cudaStream_t)stream);
+}
+
+int msl_png_unfilter(uint8_t* raw, const uint64_t* raw_off, int n, int H, int W, int bytes_per_pixel, uint8_t* out, uint32_t* status,
+                     msl_stream_t stream) {
+    MSL_REQUIRE(n >= 0 && H > 0 && W > 0, "non-positive size");
+    MSL_REQUIRE(bytes_per_pixel >= 1 && bytes_per_pixel <= 4, "bytes_per_pixel %d no válido (1..4)", bytes_per_pixel);
+    if (n == 0) return MSL_OK;
+    MSL_REQUIRE(raw && raw_off && out && status, "NULL pointer");
+    return launch_png_unfilter(raw, reinterpret_cast<const unsigned long long*>(raw_off), n, H, W, bytes_per_pixel, out, status,
+                               (cudaStream_t)stream);
+}
+
+int msl_nifti_convert(const uint8_t* payload, int datatype, uint64_t nvox, double slope, double inter, int scaled, float* out_f32,
+                      uint8_t* out_u8, uint64_t* inexact, msl_stream_t stream) {
+    MSL_REQUIRE(payload && inexact && (out_f32 || out_u8), "NULL pointer");
+    switch (datatype) {
+        case 2: case 4: case 8: case 16: case 64: case 256: case 512: case 768: break;
+        default: set_error("NIfTI datatype %d not supported", datatype); return MSL_ERR_UNSUPPORTED;
+    }
+    return launch_nifti_convert(payload, datatype, nvox, slope, inter, scaled, out_f32, out_u8,
+                                reinterpret_cast<unsigned long long*>(inexact), (cudaStream_t)stream);
+}
+
 int msl_nonzero_flags(const uint8_t* stack, int nvol, int A, int B, int C, uint8_t* any_a, uint8_t* any_b, msl_stream_t stream) {
     MSL_REQUIRE(stack && any_a && any_b, "NULL pointer");
     MSL_REQUIRE(nvol > 0 && A > 0 && B > 0 && C > 0, "non-positive size");

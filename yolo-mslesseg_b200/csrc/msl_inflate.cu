@@ -1,0 +1,438 @@
+// Byte-stream codec on the device, decode side: RFC 1951 inflate (stored, fixed and dynamic blocks)
+// of many independent streams - the .nii.gz volumes behind nib.load (utils/Paciente.py:168, utils/utils.py:156) and the
+// zlib streams inside the predicted-mask PNGs behind Image.open / cv2.imread (scripts/reconstruir_volumen.py:141,
+// utils/utils.py:391) - so that the host-to-device copies carry file bytes.
+//
+// inflate_kernel: ONE WARP per stream.  Huffman decoding is serial by nature, so parallelism comes from the number of
+//   streams (a .nii.gz written by msl_deflate_chunks is ~450 independent members per volume; a patient has hundreds of
+//   mask PNGs).  Every lane runs the same decode loop on the same bit buffer (loads and table look-ups are broadcasts, no
+//   divergence); literals are collected one per lane and stored 32 at a time; a match is copied by the whole warp
+//   (out[pos + i] = out[pos - dist + i mod dist]).  Decoding goes through a 10-bit (literal / length) and an 8-bit
+//   (distance) look-up table in shared memory, longer codes through the canonical count / symbol walk.
+// png_unfilter_kernel: PNG scanline filters 0-4 (None, Sub, Up, Average, Paeth) undone by one warp per image, then the
+//   first channel is written out as the uint8 mask image msl_recon consumes.
+// nifti_convert_kernel: voxel payload of a NIfTI-1 file (uint8 / int16 / int32 / float32 / float64, little endian) -> the
+//   float32 or uint8 volume the kernels consume, with the count of values the conversion could not represent exactly.
+#include <cstring>
+
+#include "msl_common.cuh"
+#include "msl_kernels.h"
+
+namespace msl {
+
+namespace {
+
+constexpr int kInfWarps = 4;
+constexpr int kLitBits = 10, kDistBits = 8;
+
+struct WarpTables {
+    uint16_t lit[1 << kLitBits];      // (symbol << 4) | code length; 0 = code longer than kLitBits
+    uint16_t dist[1 << kDistBits];    // also the code-length code's table while a dynamic header is read
+    uint16_t lit_sorted[288], dist_sorted[32];
+    uint16_t codes[320];
+    int lit_count[16], dist_count[16];
+    int next_code[16], offs[16];
+    uint8_t lens[384];                // [0, 19): code-length code; [32, 32 + HLIT + HDIST): literal / length and distance lengths
+};
+
+struct InfArgs {
+    const uint8_t* src;
+    const unsigned long long* src_off;   // [n + 1]
+    uint8_t* dst;
+    const unsigned long long* dst_off;   // [n + 1]
+    uint32_t* status;                    // [n][4]: error, bytes produced, stored checksum (Adler-32 / CRC-32 of the last member), stored ISIZE
+    int n, container;
+    unsigned long long src_bytes;        // readable bytes at src (loads are clamped to it)
+};
+
+enum { INF_OK = 0, INF_ERR_HEADER = 1, INF_ERR_BLOCK = 2, INF_ERR_CODE = 3, INF_ERR_DIST = 4, INF_ERR_SPACE = 5, INF_ERR_INPUT = 6 };
+
+struct BitReader {
+    const uint32_t* w;              // src as aligned words
+    unsigned long long nwords;      // words that may be read
+    unsigned long long next;        // index of the next word to load
+    unsigned long long bb;
+    int nb;
+    __device__ __forceinline__ void init(const uint8_t* src, unsigned long long src_bytes, unsigned long long bytepos) {
+        w = reinterpret_cast<const uint32_t*>(src);
+        nwords = (src_bytes + 3) >> 2;
+        next = bytepos >> 2;
+        bb = 0; nb = 0;
+        refill();
+        const int drop = (int)(bytepos & 3) * 8;
+        bb >>= drop; nb -= drop;
+        refill();
+    }
+    __device__ __forceinline__ void refill() {
+        if (nb <= 32) {
+            const uint32_t v = next < nwords ? __ldg(w + next) : 0u;
+            bb |= (unsigned long long)v << nb;
+            nb += 32; ++next;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)bb & ((1u << n) - 1u); }
+    __device__ __forceinline__ void drop(int n) { bb >>= n; nb -= n; }
+    __device__ __forceinline__ uint32_t take(int n) { const uint32_t v = peek(n); drop(n); return v; }
+    __device__ __forceinline__ unsigned long long bitpos() const { return next * 32ull - (unsigned long long)nb; }
+};
+
+// canonical Huffman tables from code lengths (all lanes call it; lane 0 does the serial part)
+__device__ void build_table(const uint8_t* lens, int n, uint16_t* fast, int fastbits, int* count, uint16_t* sorted, uint16_t* codes,
+                            int* next_code, int* offs, int lane) {
+    for (int i = lane; i < (1 << fastbits); i += 32) fast[i] = 0;
+    if (lane < 16) count[lane] = 0;
+    __syncwarp();
+    for (int s = lane; s < n; s += 32) if (lens[s]) atomicAdd(&count[lens[s]], 1);
+    __syncwarp();
+    if (lane == 0) {
+        int code = 0, o = 0;
+        for (int b = 1; b <= 15; ++b) { code = (code + (b > 1 ? count[b - 1] : 0)) << 1; next_code[b] = code; offs[b] = o; o += count[b]; }
+        for (int s = 0; s < n; ++s) {
+            const int l = lens[s];
+            if (l) { codes[s] = (uint16_t)next_code[l]++; sorted[offs[l]++] = (uint16_t)s; }
+        }
+    }
+    __syncwarp();
+    for (int s = lane; s < n; s += 32) {
+        const int l = lens[s];
+        if (l && l <= fastbits) {
+            const uint32_t rev = __brev((uint32_t)codes[s]) >> (32 - l);
+            const uint16_t e = (uint16_t)((s << 4) | l);
+            for (uint32_t k = rev; k < (1u << fastbits); k += 1u << l) fast[k] = e;
+        }
+    }
+    __syncwarp();
+}
+
+// decode one symbol; returns -1 when no code matches
+__device__ __forceinline__ int decode_sym(BitReader& br, const uint16_t* fast, int fastbits, const int* count, const uint16_t* sorted) {
+    const uint32_t e = fast[br.peek(fastbits)];
+    if (e) { br.drop((int)(e & 15u)); return (int)(e >> 4); }
+    // canonical walk (codes longer than the look-up table)
+    int code = 0, first = 0, index = 0;
+    unsigned long long b = br.bb;
+    for (int len = 1; len <= 15; ++len) {
+        code |= (int)(b & 1ull); b >>= 1;
+        const int c = count[len];
+        if (code - c < first) { br.drop(len); return sorted[index + (code - first)]; }
+        index += c; first += c; first <<= 1; code <<= 1;
+    }
+    return -1;
+}
+
+__constant__ uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ uint8_t kClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+__global__ void __launch_bounds__(kInfWarps * 32) inflate_kernel(const InfArgs a) {
+    __shared__ WarpTables tabs[kInfWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = blockIdx.x * kInfWarps + warp;
+    if (s >= a.n) return;
+    WarpTables& T = tabs[warp];
+    const unsigned long long sbeg = a.src_off[s], send = a.src_off[s + 1];
+    uint8_t* out = a.dst + a.dst_off[s];
+    const unsigned long long cap = a.dst_off[s + 1] - a.dst_off[s];
+    unsigned long long pos = 0;
+    int err = INF_OK;
+    uint32_t stored_chk = 0, stored_isize = 0;
+    unsigned long long bytepos = sbeg;
+
+    // pending literals: one per lane, stored 32 at a time
+    int pend = 0;
+    uint32_t mylit = 0;
+    auto flush = [&]() {
+        if (pend) {
+            if (pos + pend > cap) { err = INF_ERR_SPACE; pend = 0; return; }
+            if (lane < pend) out[pos + lane] = (uint8_t)mylit;
+            pos += pend; pend = 0;
+            __syncwarp();
+        }
+    };
+
+    for (;;) {      // members (gzip files may hold several)
+        // ---- container header
+        if (a.container == MSL_Z_ZLIB) {
+            if (send - bytepos < 6) { err = INF_ERR_HEADER; break; }
+            const uint32_t cmf = a.src[bytepos], flg = a.src[bytepos + 1];
+            if ((cmf & 15u) != 8 || ((cmf << 8) | flg) % 31u != 0 || (flg & 0x20u)) { err = INF_ERR_HEADER; break; }
+            bytepos += 2;
+        } else if (a.container == MSL_Z_GZIP) {
+            if (send - bytepos < 18 || a.src[bytepos] != 0x1f || a.src[bytepos + 1] != 0x8b || a.src[bytepos + 2] != 8) { err = INF_ERR_HEADER; break; }
+            const uint32_t flg = a.src[bytepos + 3];
+            unsigned long long p = bytepos + 10;
+            if (flg & 4u) { const uint32_t xlen = a.src[p] | ((uint32_t)a.src[p + 1] << 8); p += 2 + xlen; }
+            if (flg & 8u) { while (p < send && a.src[p]) ++p; ++p; }
+            if (flg & 16u) { while (p < send && a.src[p]) ++p; ++p; }
+            if (flg & 2u) p += 2;
+            if (p + 8 > send) { err = INF_ERR_HEADER; break; }
+            bytepos = p;
+        }
+        BitReader br;
+        br.init(a.src, a.src_bytes, bytepos);
+        bool fixed_ready = false;
+        // ---- blocks
+        for (;;) {
+            br.refill();
+            const uint32_t bfinal = br.take(1), btype = br.take(2);
+            if (btype == 0) {
+                // stored: skip to the byte boundary, LEN, NLEN, then a warp copy
+                unsigned long long bp = (br.bitpos() + 7) >> 3;
+                if (bp + 4 > send) { err = INF_ERR_INPUT; break; }
+                const uint32_t len = a.src[bp] | ((uint32_t)a.src[bp + 1] << 8), nlen = a.src[bp + 2] | ((uint32_t)a.src[bp + 3] << 8);
+                if ((len ^ nlen) != 0xffffu) { err = INF_ERR_BLOCK; break; }
+                bp += 4;
+                if (bp + len > send) { err = INF_ERR_INPUT; break; }
+                flush();
+                if (err || pos + len > cap) { err = INF_ERR_SPACE; break; }
+                for (uint32_t i = lane; i < len; i += 32) out[pos + i] = a.src[bp + i];
+                __syncwarp();
+                pos += len;
+                br.init(a.src, a.src_bytes, bp + len);
+            } else if (btype == 3) {
+                err = INF_ERR_BLOCK; break;
+            } else {
+                if (btype == 1) {
+                    if (!fixed_ready) {
+                        for (int i = lane; i < 288; i += 32) T.lens[i] = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8));
+                        if (lane < 32) T.lens[288 + lane] = 5;
+                        __syncwarp();
+                        build_table(T.lens, 288, T.lit, kLitBits, T.lit_count, T.lit_sorted, T.codes, T.next_code, T.offs, lane);
+                        build_table(T.lens + 288, 30, T.dist, kDistBits, T.dist_count, T.dist_sorted, T.codes, T.next_code, T.offs, lane);
+                        fixed_ready = true;
+                    }
+                } else {
+                    fixed_ready = false;
+                    br.refill();
+                    const int hlit = (int)br.take(5) + 257, hdist = (int)br.take(5) + 1, hclen = (int)br.take(4) + 4;
+                    if (hlit > 286 || hdist > 30) { err = INF_ERR_BLOCK; break; }
+                    if (lane < 19) T.lens[lane] = 0;
+                    __syncwarp();
+                    for (int i = 0; i < hclen; ++i) {
+                        br.refill();
+                        const uint32_t v = br.take(3);
+                        if (lane == 0) T.lens[kClOrder[i]] = (uint8_t)v;
+                    }
+                    __syncwarp();
+                    // the code-length code: 7-bit look-up table in the distance table's storage
+                    build_table(T.lens, 19, T.dist, 7, T.dist_count, T.dist_sorted, T.codes, T.next_code, T.offs, lane);
+                    int i = 0;
+                    const int ntot = hlit + hdist;
+                    int prev = 0;
+                    bool bad = false;
+                    while (i < ntot) {
+                        br.refill();
+                        const int sym = decode_sym(br, T.dist, 7, T.dist_count, T.dist_sorted);
+                        if (sym < 0) { bad = true; break; }
+                        if (sym < 16) { if (lane == 0) T.lens[32 + i] = (uint8_t)sym; prev = sym; ++i; }
+                        else {
+                            int rep, val = 0;
+                            if (sym == 16) { if (i == 0) { bad = true; break; } rep = 3 + (int)br.take(2); val = prev; }
+                            else if (sym == 17) { rep = 3 + (int)br.take(3); prev = 0; }
+                            else { rep = 11 + (int)br.take(7); prev = 0; }
+                            if (i + rep > ntot) { bad = true; break; }
+                            for (int k = lane; k < rep; k += 32) T.lens[32 + i + k] = (uint8_t)val;
+                            i += rep;
+                        }
+                    }
+                    if (bad) { err = INF_ERR_BLOCK; break; }
+                    __syncwarp();
+                    // lens[32 ..): literal / length lengths, then distance lengths (moved down so that both tables index from 0)
+                    build_table(T.lens + 32, hlit, T.lit, kLitBits, T.lit_count, T.lit_sorted, T.codes, T.next_code, T.offs, lane);
+                    build_table(T.lens + 32 + hlit, hdist, T.dist, kDistBits, T.dist_count, T.dist_sorted, T.codes, T.next_code, T.offs, lane);
+                }
+                // ---- symbols
+                for (;;) {
+                    br.refill();
+                    const int sym = decode_sym(br, T.lit, kLitBits, T.lit_count, T.lit_sorted);
+                    if (sym < 256) {
+                        if (sym < 0) { err = INF_ERR_CODE; break; }
+                        if (lane == pend) mylit = (uint32_t)sym;
+                        if (++pend == 32) {
+                            flush();
+                            if (err) break;
+                        }
+                        continue;
+                    }
+                    if (sym == 256) break;
+                    if (sym > 285) { err = INF_ERR_CODE; break; }
+                    const int li = sym - 257;
+                    const int len = (int)kLenBase[li] + (int)br.take(kLenExtra[li]);
+                    br.refill();
+                    const int ds = decode_sym(br, T.dist, kDistBits, T.dist_count, T.dist_sorted);
+                    if (ds < 0 || ds > 29) { err = INF_ERR_CODE; break; }
+                    br.refill();
+                    const unsigned dist = (unsigned)kDistBase[ds] + br.take(kDistExtra[ds]);
+                    if (pos + pend + len > cap) { err = INF_ERR_SPACE; break; }
+                    flush();
+                    if (err) break;
+                    if (dist > pos) { err = INF_ERR_DIST; break; }
+                    const uint8_t* from = out + pos - dist;
+                    if (dist >= (unsigned)len) {
+                        for (int i = lane; i < len; i += 32) out[pos + i] = from[i];
+                    } else if (dist == 1) {
+                        const uint8_t v = from[0];
+                        for (int i = lane; i < len; i += 32) out[pos + i] = v;
+                    } else {
+                        for (int i = lane; i < len; i += 32) out[pos + i] = from[(unsigned)i % dist];
+                    }
+                    __syncwarp();
+                    pos += len;
+                }
+                if (err) break;
+            }
+            if (br.bitpos() > send * 8ull) { err = INF_ERR_INPUT; break; }
+            if (bfinal) { bytepos = (br.bitpos() + 7) >> 3; break; }
+        }
+        if (err) break;
+        flush();
+        if (err) break;
+        // ---- trailer
+        if (a.container == MSL_Z_ZLIB) {
+            if (bytepos + 4 > send) { err = INF_ERR_INPUT; break; }
+            stored_chk = ((uint32_t)a.src[bytepos] << 24) | ((uint32_t)a.src[bytepos + 1] << 16) | ((uint32_t)a.src[bytepos + 2] << 8) | a.src[bytepos + 3];
+            break;
+        }
+        if (a.container == MSL_Z_GZIP) {
+            if (bytepos + 8 > send) { err = INF_ERR_INPUT; break; }
+            stored_chk = a.src[bytepos] | ((uint32_t)a.src[bytepos + 1] << 8) | ((uint32_t)a.src[bytepos + 2] << 16) | ((uint32_t)a.src[bytepos + 3] << 24);
+            stored_isize = a.src[bytepos + 4] | ((uint32_t)a.src[bytepos + 5] << 8) | ((uint32_t)a.src[bytepos + 6] << 16) | ((uint32_t)a.src[bytepos + 7] << 24);
+            bytepos += 8;
+            if (bytepos + 18 <= send && a.src[bytepos] == 0x1f && a.src[bytepos + 1] == 0x8b) continue;    // next member
+        }
+        break;
+    }
+    if (lane == 0) {
+        uint32_t* st = a.status + 4 * (size_t)s;
+        st[0] = (uint32_t)err; st[1] = (uint32_t)pos; st[2] = stored_chk; st[3] = stored_isize;
+    }
+}
+
+// ---- PNG scanline filters (PNG 1.2 section 6) undone in place, one warp per image; then channel 0 -> out
+struct PngArgs2 {
+    uint8_t* raw;                        // inflated scanlines of all images
+    const unsigned long long* raw_off;   // [n + 1]
+    uint8_t* out;                        // [n][H][W] first channel
+    int n, H, W, bpp;                    // bpp = bytes per pixel (1, 2, 3, 4)
+    uint32_t* status;                    // [n]: 0 ok, 1 bad filter type / short data
+};
+
+__device__ __forceinline__ int paeth(int a, int b, int c) {
+    const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+
+__global__ void __launch_bounds__(128) png_unfilter_kernel(const PngArgs2 a) {
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (s >= a.n) return;
+    uint8_t* raw = a.raw + a.raw_off[s];
+    const unsigned long long have = a.raw_off[s + 1] - a.raw_off[s];
+    const int rb = a.W * a.bpp, bpp = a.bpp;
+    uint8_t* out = a.out + (size_t)s * a.H * a.W;
+    if (have < (unsigned long long)a.H * (rb + 1)) { if (lane == 0) a.status[s] = 1; return; }
+    uint32_t bad = 0;
+    for (int y = 0; y < a.H; ++y) {
+        uint8_t* cur = raw + (size_t)y * (rb + 1) + 1;
+        const uint8_t* up = y ? cur - (rb + 1) : nullptr;
+        const int ft = cur[-1];
+        if (ft == 1) {
+            // Sub: prefix sums (mod 256) along the scanline, one channel at a time, 32 pixels per step with a running carry
+            for (int ch = 0; ch < bpp; ++ch) {
+                int carry = 0;
+                for (int x0 = 0; x0 < a.W; x0 += 32) {
+                    const int x = x0 + lane;
+                    int v = x < a.W ? cur[x * bpp + ch] : 0;
+                    v = warp_incl_scan(v, lane) + carry;
+                    if (x < a.W) cur[x * bpp + ch] = (uint8_t)v;
+                    carry = __shfl_sync(FULL, v, 31) & 0xff;
+                }
+            }
+        } else if (ft == 2) {
+            if (up) for (int i = lane; i < rb; i += 32) cur[i] = (uint8_t)(cur[i] + up[i]);
+        } else if (ft == 3 || ft == 4) {
+            // Average / Paeth: serial along the scanline (every byte needs its reconstructed left neighbour)
+            if (lane == 0) {
+                for (int i = 0; i < rb; ++i) {
+                    const int l = i >= bpp ? cur[i - bpp] : 0, u = up ? up[i] : 0, ul = (up && i >= bpp) ? up[i - bpp] : 0;
+                    cur[i] = (uint8_t)(cur[i] + (ft == 3 ? ((l + u) >> 1) : paeth(l, u, ul)));
+                }
+            }
+        } else if (ft != 0) bad = 1;
+        __syncwarp();
+        for (int x = lane; x < a.W; x += 32) out[(size_t)y * a.W + x] = cur[x * bpp];
+    }
+    if (lane == 0) a.status[s] = bad;
+}
+
+// ---- NIfTI voxel payload -> float32 / uint8 volume
+template <typename T> __device__ __forceinline__ double load_unaligned(const uint8_t* p) {
+    T v;
+    memcpy(&v, p, sizeof(T));
+    return (double)v;
+}
+
+__global__ void nifti_convert_kernel(const uint8_t* payload, int datatype, unsigned long long nvox, double slope, double inter, int scaled,
+                                     float* out_f32, uint8_t* out_u8, unsigned long long* inexact) {
+    unsigned long long bad = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nvox; i += (unsigned long long)gridDim.x * blockDim.x) {
+        double v;
+        switch (datatype) {
+            case 2: v = (double)payload[i]; break;
+            case 4: v = load_unaligned<int16_t>(payload + 2 * i); break;
+            case 8: v = load_unaligned<int32_t>(payload + 4 * i); break;
+            case 16: v = load_unaligned<float>(payload + 4 * i); break;
+            case 64: v = load_unaligned<double>(payload + 8 * i); break;
+            case 256: v = (double)(int8_t)payload[i]; break;
+            case 512: v = load_unaligned<uint16_t>(payload + 2 * i); break;
+            case 768: v = load_unaligned<uint32_t>(payload + 4 * i); break;
+            default: v = 0.0; break;
+        }
+        if (scaled) v = v * slope + inter;
+        if (out_f32) { const float f = (float)v; out_f32[i] = f; if ((double)f != v && v == v) ++bad; }
+        if (out_u8) { const int q = (v >= 0.0 && v <= 255.0) ? (int)v : 0; out_u8[i] = (uint8_t)q; if ((double)q != v) ++bad; }
+    }
+    bad = __reduce_add_sync(FULL, (unsigned)bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(inexact, bad);
+}
+
+}  // namespace
+
+int launch_inflate(const uint8_t* src, size_t src_bytes, const unsigned long long* src_off, int n, int container, uint8_t* dst,
+                   const unsigned long long* dst_off, uint32_t* status, cudaStream_t stream) {
+    if (n <= 0) return MSL_OK;
+    if (reinterpret_cast<uintptr_t>(src) & 3) { set_error("inflate: src must be 4-byte aligned"); return MSL_ERR_ARG; }
+    InfArgs a;
+    a.src = src; a.src_off = src_off; a.dst = dst; a.dst_off = dst_off; a.status = status; a.n = n; a.container = container;
+    a.src_bytes = src_bytes;
+    ProfScope prof(K_INFLATE, stream);
+    inflate_kernel<<<(n + kInfWarps - 1) / kInfWarps, kInfWarps * 32, 0, stream>>>(a);
+    MSL_LAUNCH_CHECK("inflate_kernel");
+    return MSL_OK;
+}
+
+int launch_png_unfilter(uint8_t* raw, const unsigned long long* raw_off, int n, int H, int W, int bpp, uint8_t* out, uint32_t* status,
+                        cudaStream_t stream) {
+    if (n <= 0) return MSL_OK;
+    PngArgs2 a;
+    a.raw = raw; a.raw_off = raw_off; a.out = out; a.n = n; a.H = H; a.W = W; a.bpp = bpp; a.status = status;
+    ProfScope prof(K_PNG_UNFILTER, stream);
+    png_unfilter_kernel<<<(n + 3) / 4, 128, 0, stream>>>(a);
+    MSL_LAUNCH_CHECK("png_unfilter_kernel");
+    return MSL_OK;
+}
+
+int launch_nifti_convert(const uint8_t* payload, int datatype, unsigned long long nvox, double slope, double inter, int scaled,
+                         float* out_f32, uint8_t* out_u8, unsigned long long* inexact, cudaStream_t stream) {
+    if (nvox == 0) return MSL_OK;
+    MSL_CUDA_CHECK(cudaMemsetAsync(inexact, 0, sizeof(unsigned long long), stream));
+    ProfScope prof(K_NIFTI_CONVERT, stream);
+    const int blocks = (int)((nvox + 256ull * 8 - 1) / (256ull * 8) < 148 * 16 ? (nvox + 256ull * 8 - 1) / (256ull * 8) : 148 * 16);
+    nifti_convert_kernel<<<blocks, 256, 0, stream>>>(payload, datatype, nvox, slope, inter, scaled, out_f32, out_u8, inexact);
+    MSL_LAUNCH_CHECK("nifti_convert_kernel");
+    return MSL_OK;
+}
+
+}  // namespace msl

@@ -27,7 +27,14 @@ enum KernelKind {
     K_PNG_PACK = 23,
     K_NONZERO_FLAGS = 24,
     K_ENH_DENSE_TABLES = 25,   // per-launch plane tables of enhance_dense
-    K_NKIND = 26
+    K_DEFLATE = 26,            // fixed-Huffman deflate of byte streams (PNG / zlib / gzip containers)
+    K_DEFLATE_SCAN = 27,
+    K_DEFLATE_PACK = 28,
+    K_INFLATE = 29,
+    K_PNG_UNFILTER = 30,
+    K_NIFTI_CONVERT = 31,
+    K_CHECKSUM = 32,
+    K_NKIND = 33
 };
 
 // RAII: counts the launch and, when profiling is enabled, brackets it with CUDA events on `stream`.
@@ -112,6 +119,19 @@ int launch_combine_predictions(const float* masks, const int32_t* inst_offset, i
 int launch_bgr_to_gray(const uint8_t* bgr, size_t npx, uint8_t* gray, cudaStream_t stream);
 size_t png_file_bytes(int H, int W, int ch);
 int launch_png_pack(const uint8_t* pixels, int n, int H, int W, int ch, uint8_t* out, size_t out_pitch, cudaStream_t stream);
+// msl_codec.cu: deflate streams in zlib / gzip / PNG containers, packed back to back
+size_t deflate_slot_bytes(int container, size_t raw);
+size_t deflate_workspace_bytes(int n, int container, size_t raw);
+int launch_deflate_pack(const uint8_t* src, int n, size_t src_pitch, size_t chunk, size_t total, int rows, int row_bytes,
+                        int img_w, int img_ch, int container, int dist2, uint8_t* out, size_t out_cap, unsigned long long* out_off,
+                        uint32_t* out_meta, void* ws, size_t ws_bytes, cudaStream_t stream);
+// msl_inflate.cu: inflate (one warp per stream), PNG unfilter, NIfTI payload conversion
+int launch_inflate(const uint8_t* src, size_t src_bytes, const unsigned long long* src_off, int n, int container, uint8_t* dst,
+                   const unsigned long long* dst_off, uint32_t* status, cudaStream_t stream);
+int launch_png_unfilter(uint8_t* raw, const unsigned long long* raw_off, int n, int H, int W, int bpp, uint8_t* out, uint32_t* status,
+                        cudaStream_t stream);
+int launch_nifti_convert(const uint8_t* payload, int datatype, unsigned long long nvox, double slope, double inter, int scaled,
+                         float* out_f32, uint8_t* out_u8, unsigned long long* inexact, cudaStream_t stream);
 int launch_nonzero_flags(const uint8_t* stack, int nvol, int A, int B, int C, uint8_t* any_a, uint8_t* any_b, cudaStream_t stream);
 int launch_slice_counts(const uint8_t* gt, const uint8_t* pred, int nvol, int X, int Y, int Z, long long* counts, cudaStream_t stream);
 int launch_consensus_eval(const uint8_t* ax, const uint8_t* co, const uint8_t* sa, const uint8_t* gt,

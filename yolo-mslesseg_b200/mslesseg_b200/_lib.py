@@ -19,6 +19,7 @@ F32, U8 = 0, 1
 OUT_G, OUT_P, OUT_PNG_GRAY, OUT_PNG_RGBA = 0, 1, 2, 3
 WS_ENHANCE_VOLUMES, WS_RECON = 1, 2
 OK, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4
+Z_RAW, Z_ZLIB, Z_GZIP, Z_PNG = 0, 1, 2, 3
 
 PLANO_ID = {"axial": AXIAL, "coronal": CORONAL, "sagital": SAGITAL}
 MEJORA_ID = {None: MEJORA_NONE, "HE": MEJORA_HE, "CLAHE": MEJORA_CLAHE, "GC": MEJORA_GC, "LT": MEJORA_LT}
@@ -43,6 +44,13 @@ _SIGNATURES = {
     "msl_enhance_volumes": (C.c_int, [_vp, _i, _i, _i, _i, C.POINTER(C.c_void_p), _vp, _vp, _sz, _vp]),
     "msl_png_bytes": (_sz, [_i, _i, _i]),
     "msl_png_pack": (C.c_int, [_vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "msl_deflate_bound": (_sz, [_i, _i, _sz]),
+    "msl_deflate_workspace_bytes": (_sz, [_i, _i, _sz]),
+    "msl_deflate_chunks": (C.c_int, [_vp, _sz, _sz, _i, _i, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
+    "msl_png_encode": (C.c_int, [_vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp, _sz, _vp]),
+    "msl_inflate": (C.c_int, [_vp, _sz, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "msl_png_unfilter": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "msl_nifti_convert": (C.c_int, [_vp, _i, C.c_uint64, C.c_double, C.c_double, _i, _vp, _vp, _vp, _vp]),
     "msl_nonzero_flags": (C.c_int, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "msl_copy_box_d2h": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "msl_copy_boxes_d2h": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),

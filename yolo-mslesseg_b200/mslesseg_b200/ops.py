@@ -346,6 +346,79 @@ def png_pack(pixels: torch.Tensor):
     return out, size
 
 
+# ------------------------------------------------------------------------------------ byte-stream codec
+_CONTAINER_ID = {"raw": L.Z_RAW, "zlib": L.Z_ZLIB, "gzip": L.Z_GZIP, "png": L.Z_PNG}
+
+
+class PackedStreams:
+    """n variable-length byte streams packed back to back on the device: stream i = data[off[i]:off[i+1]] (off: uint64
+    [n + 1], device).  `to_host()` brings offsets and bytes to the host (two copies: the offsets tell how many bytes)."""
+
+    def __init__(self, data: torch.Tensor, off: torch.Tensor, meta: Optional[torch.Tensor] = None):
+        self.data, self.off, self.meta = data, off, meta
+
+    def to_host(self, pinned: Optional[torch.Tensor] = None):
+        """(bytes ndarray of the packed streams, offsets ndarray int64 [n + 1])."""
+        off = self.off.cpu().numpy().astype(np.int64)
+        total = int(off[-1])
+        if total > self.data.numel():
+            raise RuntimeError(f"packed streams need {total} bytes, capacity was {self.data.numel()}")
+        if pinned is not None:
+            pinned[:total].copy_(self.data[:total], non_blocking=False)
+            return pinned[:total].numpy(), off
+        return self.data[:total].cpu().numpy(), off
+
+    def files(self):
+        data, off = self.to_host()
+        return [data[off[i]:off[i + 1]].tobytes() for i in range(len(off) - 1)]
+
+
+def deflate_chunks(src: torch.Tensor, chunk_len: int = 65536, container: str = "gzip", dist2: int = 0,
+                   out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> PackedStreams:
+    """Cuts the bytes of `src` (any contiguous CUDA tensor) into chunks of chunk_len bytes and deflates every chunk into
+    its own stream (container "raw", "zlib" or "gzip").  The concatenation of the gzip members is a valid .gz file of the
+    whole buffer (reference utils/utils.py:176-177 nib.save -> gzip)."""
+    _need_cuda(src, "src")
+    lib = L.load()
+    cid = _CONTAINER_ID[container]
+    total = src.numel() * src.element_size()
+    n = max(1, -(-total // chunk_len))
+    cap = int(lib.msl_deflate_bound(n, cid, chunk_len))
+    if out is None:
+        out = torch.empty(cap, dtype=torch.uint8, device=src.device)
+    need = int(lib.msl_deflate_workspace_bytes(n, cid, chunk_len))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=src.device)
+    off = torch.empty(n + 1, dtype=torch.int64, device=src.device)
+    meta = torch.empty((n, 4), dtype=torch.int32, device=src.device)
+    L.check(lib.msl_deflate_chunks(_ptr(src), total, chunk_len, cid, dist2, _ptr(out), out.numel(), _ptr(off), _ptr(meta),
+                                   _ptr(workspace), workspace.numel(), _stream()))
+    return PackedStreams(out, off, meta)
+
+
+def png_encode(pixels: torch.Tensor, out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> PackedStreams:
+    """Compressed PNG files for a batch of images: uint8 [n, H, W, C] (C = 4 RGBA - what plt.imsave writes, reference
+    scripts/extraer_dataset.py:192,197 - or 2 / 3) or [n, H, W] (gray, what cv2.imwrite writes for masks).  The files are
+    packed back to back on the device (PackedStreams)."""
+    _need_cuda(pixels, "pixels")
+    if pixels.dtype != torch.uint8 or pixels.dim() not in (3, 4) or (pixels.dim() == 4 and not 1 <= pixels.shape[-1] <= 4):
+        raise ValueError("pixels must be uint8 [n, H, W, C] (C <= 4) or [n, H, W]")
+    pixels = pixels.contiguous()
+    n, H, W = (int(d) for d in pixels.shape[:3])
+    ch = int(pixels.shape[3]) if pixels.dim() == 4 else 1
+    lib = L.load()
+    raw = H * (W * ch + 1)
+    cap = int(lib.msl_deflate_bound(max(n, 1), L.Z_PNG, raw))
+    if out is None:
+        out = torch.empty(cap, dtype=torch.uint8, device=pixels.device)
+    need = int(lib.msl_deflate_workspace_bytes(max(n, 1), L.Z_PNG, raw))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=pixels.device)
+    off = torch.zeros(n + 1, dtype=torch.int64, device=pixels.device)
+    L.check(lib.msl_png_encode(_ptr(pixels), n, H, W, ch, _ptr(out), out.numel(), _ptr(off), _ptr(workspace), workspace.numel(), _stream()))
+    return PackedStreams(out, off)
+
+
 # ------------------------------------------------------------------------------------ host hand-off
 def nonzero_flags(stack: torch.Tensor, out=None):
     """Which slices and rows of a uint8 stack [nvol, A, B, C] hold a non-zero byte: (any_a [nvol, A], any_b [nvol, B]).
