@@ -349,13 +349,13 @@ int msl_png_unfilter(uint8_t* raw, const uint64_t* raw_off, int n, int H, int W,
 }
 
 int msl_nifti_convert(const uint8_t* payload, int datatype, uint64_t nvox, double slope, double inter, int scaled, float* out_f32,
-                      uint8_t* out_u8, uint64_t* inexact, msl_stream_t stream) {
-    MSL_REQUIRE(payload && inexact && (out_f32 || out_u8), "NULL pointer");
+                      uint8_t* out_u8, double* out_f64, uint64_t* inexact, msl_stream_t stream) {
+    MSL_REQUIRE(payload && inexact && (out_f32 || out_u8 || out_f64), "NULL pointer");
     switch (datatype) {
         case 2: case 4: case 8: case 16: case 64: case 256: case 512: case 768: break;
         default: set_error("NIfTI datatype %d not supported", datatype); return MSL_ERR_UNSUPPORTED;
     }
-    return launch_nifti_convert(payload, datatype, nvox, slope, inter, scaled, out_f32, out_u8,
+    return launch_nifti_convert(payload, datatype, nvox, slope, inter, scaled, out_f32, out_u8, out_f64,
                                 reinterpret_cast<unsigned long long*>(inexact), (cudaStream_t)stream);
 }
 

@@ -375,7 +375,7 @@ template <typename T> __device__ __forceinline__ double load_unaligned(const uin
 }
 
 __global__ void nifti_convert_kernel(const uint8_t* payload, int datatype, unsigned long long nvox, double slope, double inter, int scaled,
-                                     float* out_f32, uint8_t* out_u8, unsigned long long* inexact) {
+                                     float* out_f32, uint8_t* out_u8, double* out_f64, unsigned long long* inexact) {
     unsigned long long bad = 0;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nvox; i += (unsigned long long)gridDim.x * blockDim.x) {
         double v;
@@ -391,6 +391,7 @@ __global__ void nifti_convert_kernel(const uint8_t* payload, int datatype, unsig
             default: v = 0.0; break;
         }
         if (scaled) v = v * slope + inter;
+        if (out_f64) out_f64[i] = v;
         if (out_f32) { const float f = (float)v; out_f32[i] = f; if ((double)f != v && v == v) ++bad; }
         if (out_u8) { const int q = (v >= 0.0 && v <= 255.0) ? (int)v : 0; out_u8[i] = (uint8_t)q; if ((double)q != v) ++bad; }
     }
@@ -425,12 +426,12 @@ int launch_png_unfilter(uint8_t* raw, const unsigned long long* raw_off, int n, 
 }
 
 int launch_nifti_convert(const uint8_t* payload, int datatype, unsigned long long nvox, double slope, double inter, int scaled,
-                         float* out_f32, uint8_t* out_u8, unsigned long long* inexact, cudaStream_t stream) {
+                         float* out_f32, uint8_t* out_u8, double* out_f64, unsigned long long* inexact, cudaStream_t stream) {
     if (nvox == 0) return MSL_OK;
     MSL_CUDA_CHECK(cudaMemsetAsync(inexact, 0, sizeof(unsigned long long), stream));
     ProfScope prof(K_NIFTI_CONVERT, stream);
     const int blocks = (int)((nvox + 256ull * 8 - 1) / (256ull * 8) < 148 * 16 ? (nvox + 256ull * 8 - 1) / (256ull * 8) : 148 * 16);
-    nifti_convert_kernel<<<blocks, 256, 0, stream>>>(payload, datatype, nvox, slope, inter, scaled, out_f32, out_u8, inexact);
+    nifti_convert_kernel<<<blocks, 256, 0, stream>>>(payload, datatype, nvox, slope, inter, scaled, out_f32, out_u8, out_f64, inexact);
     MSL_LAUNCH_CHECK("nifti_convert_kernel");
     return MSL_OK;
 }

@@ -131,7 +131,7 @@ int launch_inflate(const uint8_t* src, size_t src_bytes, const unsigned long lon
 int launch_png_unfilter(uint8_t* raw, const unsigned long long* raw_off, int n, int H, int W, int bpp, uint8_t* out, uint32_t* status,
                         cudaStream_t stream);
 int launch_nifti_convert(const uint8_t* payload, int datatype, unsigned long long nvox, double slope, double inter, int scaled,
-                         float* out_f32, uint8_t* out_u8, unsigned long long* inexact, cudaStream_t stream);
+                         float* out_f32, uint8_t* out_u8, double* out_f64, unsigned long long* inexact, cudaStream_t stream);
 int launch_nonzero_flags(const uint8_t* stack, int nvol, int A, int B, int C, uint8_t* any_a, uint8_t* any_b, cudaStream_t stream);
 int launch_slice_counts(const uint8_t* gt, const uint8_t* pred, int nvol, int X, int Y, int Z, long long* counts, cudaStream_t stream);
 int launch_consensus_eval(const uint8_t* ax, const uint8_t* co, const uint8_t* sa, const uint8_t* gt,

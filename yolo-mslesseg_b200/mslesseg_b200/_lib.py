@@ -50,7 +50,7 @@ _SIGNATURES = {
     "msl_png_encode": (C.c_int, [_vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp, _sz, _vp]),
     "msl_inflate": (C.c_int, [_vp, _sz, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "msl_png_unfilter": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "msl_nifti_convert": (C.c_int, [_vp, _i, C.c_uint64, C.c_double, C.c_double, _i, _vp, _vp, _vp, _vp]),
+    "msl_nifti_convert": (C.c_int, [_vp, _i, C.c_uint64, C.c_double, C.c_double, _i, _vp, _vp, _vp, _vp, _vp]),
     "msl_nonzero_flags": (C.c_int, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "msl_copy_box_d2h": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "msl_copy_boxes_d2h": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),

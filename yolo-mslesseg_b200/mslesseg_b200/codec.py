@@ -184,9 +184,10 @@ def nifti_read_header(path):
 
 
 def nifti_load_device(path, device, dtype=torch.float32):
-    """(volume [Z][Y][X] on the device as float32 or uint8, shape (X, Y, Z), affine).  The file bytes are uploaded as they
-    are; inflate + datatype conversion (+ scl_slope / scl_inter) run on the GPU.  uint8 output demands integral values in
-    0..255 (masks); float32 output demands float32-representable values - otherwise CodecError."""
+    """(volume [Z][Y][X] on the device as float32, uint8 or float64, shape (X, Y, Z), affine).  The file bytes are uploaded
+    as they are; inflate + datatype conversion (+ scl_slope / scl_inter) run on the GPU.  uint8 output demands integral
+    values in 0..255 (masks); float32 output demands float32-representable values - otherwise CodecError; float64 holds
+    whatever nib.load(path).get_fdata() yields."""
     path = str(path)
     data = Path(path).read_bytes()
     dev = torch.device(device)
@@ -220,7 +221,8 @@ def nifti_load_device(path, device, dtype=torch.float32):
     payload = raw[vox_offset:]
     L.check(L.load().msl_nifti_convert(ops._ptr(payload), datatype, nvox, slope, inter, 1 if scaled else 0,
                                        ops._ptr(out) if dtype == torch.float32 else None,
-                                       ops._ptr(out) if dtype == torch.uint8 else None, ops._ptr(inexact), ops._stream()))
+                                       ops._ptr(out) if dtype == torch.uint8 else None,
+                                       ops._ptr(out) if dtype == torch.float64 else None, ops._ptr(inexact), ops._stream()))
     bad = int(inexact.item())
     if bad:
         raise CodecError(f"{path}: {bad} voxels are not representable as {dtype}")
@@ -248,15 +250,16 @@ def nifti_header_bytes(shape_xyz, np_dtype, affine) -> bytes:
 
 
 def nifti_gz_device(vol_zyx: torch.Tensor, affine, dist2: Optional[int] = None) -> ops.PackedStreams:
-    """The bytes of a .nii.gz file for a device volume [Z][Y][X] (float32 or uint8): header + voxels deflated on the GPU in
+    """The bytes of a .nii.gz file for a device volume [Z][Y][X] (float32, uint8, float64, int16, int32, int8): header + voxels deflated on the GPU in
     64 KB members (reference utils/utils.py:173-181 guardar_volumen).  `b"".join(ps.files())` / ps.to_host() is the file."""
     ops._need_cuda(vol_zyx, "vol_zyx")
     Z, Y, X = (int(d) for d in vol_zyx.shape)
-    npdt = {torch.float32: np.float32, torch.uint8: np.uint8}[vol_zyx.dtype]
+    npdt = {torch.float32: np.float32, torch.uint8: np.uint8, torch.float64: np.float64, torch.int16: np.int16,
+            torch.int32: np.int32, torch.int8: np.int8}[vol_zyx.dtype]
     hdr = torch.from_numpy(np.frombuffer(nifti_header_bytes((X, Y, Z), npdt, affine), np.uint8).copy()).to(vol_zyx.device)
-    buf = torch.cat([hdr, vol_zyx.reshape(-1).view(torch.uint8)])
+    buf = torch.cat([hdr, vol_zyx.contiguous().reshape(-1).view(torch.uint8)])
     if dist2 is None:
-        dist2 = 4 if vol_zyx.dtype == torch.float32 else 0
+        dist2 = vol_zyx.element_size() if vol_zyx.element_size() > 1 else 0
     return ops.deflate_chunks(buf, chunk_len=CHUNK, container="gzip", dist2=dist2)
 
 

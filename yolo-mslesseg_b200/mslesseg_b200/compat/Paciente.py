@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from .. import metrics as _M
-from .. import nifti as _nifti
+from .. import codec as _codec
 from .. import ops
 from . import device
 from .utils import ruta_existente
@@ -74,7 +74,8 @@ class Paciente:
             vol_path = self.volumen_path(modalidad)
             if not ruta_existente(vol_path):
                 raise FileNotFoundError(f"No se encontró el volumen {modalidad}.")
-            self._volumenes[modalidad] = _nifti.load(vol_path, np.float64)[0]
+            # decoded on the GPU (the device copy is kept: it is what the enhancement kernels read)
+            self._volumenes[modalidad] = np.asfortranarray(self._vol_dev(modalidad)[0].cpu().numpy().astype(np.float64).transpose(2, 1, 0))
         return self._volumenes[modalidad]
 
     @property
@@ -82,7 +83,8 @@ class Paciente:
         if self._gt_mask is None:
             if not ruta_existente(self.gt_mask_path):
                 raise FileNotFoundError(f"No se encontró la máscara en {self.gt_mask_path}")
-            self._gt_mask = _nifti.load(self.gt_mask_path, np.float64)[0]
+            g = _codec.nifti_load_device(self.gt_mask_path, device(), torch.float64)[0]
+            self._gt_mask = np.asfortranarray(g.cpu().numpy().transpose(2, 1, 0))
         return self._gt_mask
 
     @property
@@ -90,6 +92,8 @@ class Paciente:
         mapping = {"axial": 2, "coronal": 1, "sagital": 0}
         if self.plano not in mapping:
             raise ValueError(f"Plano no reconocido: {self.plano}")
+        if self._gt_mask is None and ruta_existente(self.gt_mask_path):
+            return _codec.nifti_read_header(self.gt_mask_path)[0][mapping[self.plano]]
         return self.gt_mask.shape[mapping[self.plano]]
 
     # ---- device residency ----
@@ -100,13 +104,28 @@ class Paciente:
         return torch.from_numpy(a).to(device())[None]
 
     def _vol_dev(self, modalidad):
+        """float32 [1, Z, Y, X] on the device.  From the file: its bytes are uploaded and inflated on the GPU (no host
+        decode); from an array the caller put into `_volumenes`: uploaded."""
         if modalidad not in self._dev:
-            self._dev[modalidad] = self._upload(self.cargar_volumen(modalidad), np.float32)
+            if modalidad in self._volumenes:
+                self._dev[modalidad] = self._upload(self._volumenes[modalidad], np.float32)
+            else:
+                vol_path = self.volumen_path(modalidad)
+                if not ruta_existente(vol_path):
+                    raise FileNotFoundError(f"No se encontró el volumen {modalidad}.")
+                self._dev[modalidad] = _codec.nifti_load_device(vol_path, device(), torch.float32)[0][None]
         return self._dev[modalidad]
 
     def _gt_dev(self):
+        """uint8 [1, Z, Y, X]: (mask > 0), the predicate of indices_cortes_con_lesion (utils/Paciente.py:256)."""
         if "gt" not in self._dev:
-            self._dev["gt"] = self._upload(np.asarray(self.gt_mask) > 0, np.uint8)
+            if self._gt_mask is not None:
+                self._dev["gt"] = self._upload(np.asarray(self._gt_mask) > 0, np.uint8)
+            else:
+                if not ruta_existente(self.gt_mask_path):
+                    raise FileNotFoundError(f"No se encontró la máscara en {self.gt_mask_path}")
+                g = _codec.nifti_load_device(self.gt_mask_path, device(), torch.float32)[0]
+                self._dev["gt"] = (g > 0).to(torch.uint8)[None]
         return self._dev["gt"]
 
     # ---- processing (utils/Paciente.py:195-246) ----

@@ -5,7 +5,7 @@ import logging
 from pathlib import Path
 
 from .. import metrics as _M
-from .utils import cargar_volumen, leer_json, metricas, reconstruccion_valida
+from .utils import cargar_volumen, cargar_volumen_dispositivo, leer_json, metricas, reconstruccion_valida
 
 logger = logging.getLogger(__name__)
 
@@ -20,7 +20,15 @@ def calcular_metricas(gt_vol_path, pred_vol_path):
     if not reconstruccion_valida(pred_vol_path, gt_vol_path):
         logger.warning(f"⚠️ Reconstrucción inválida: {Path(pred_vol_path).name}")
         return {}
-    return generar_diccionario_metricas(cargar_volumen(gt_vol_path), cargar_volumen(pred_vol_path))
+    # both files are inflated on the GPU as uint8 masks (non-integral / out-of-range voxels raise) and counted there
+    import torch
+    from .. import ops
+    gt = cargar_volumen_dispositivo(gt_vol_path, torch.uint8).reshape(1, -1)
+    pred = cargar_volumen_dispositivo(pred_vol_path, torch.uint8).reshape(1, -1)
+    c = ops.confusion_counts(gt, pred)[0].cpu().numpy()
+    if int(c.sum()) != gt.numel():
+        return generar_diccionario_metricas(cargar_volumen(gt_vol_path), cargar_volumen(pred_vol_path))   # non-binary masks: exact == 1 / == 0 predicates
+    return _M.metricas_desde_conteos(*(int(x) for x in c))
 
 
 calcular_promedio = _M.calcular_promedio

@@ -32,13 +32,13 @@ def resolver_num_cortes(num_cortes, input_dir, plano, modalidad):
 
 
 def _escribir_pngs(rgba_dev, rutas):
-    """One PNG file per image of the device stack [n, H, W, 4]: the files are assembled on the GPU (ops.png_pack: stored
-    deflate blocks, CRC-32 / Adler-32 computed in the kernel), the host only writes the bytes."""
-    files, size = ops.png_pack(rgba_dev)
-    host = files.cpu().numpy()
+    """One PNG file per image of the device stack [n, H, W, 4]: the files are deflated and assembled on the GPU
+    (ops.png_encode: fixed-Huffman deflate with run matches, Adler-32 / CRC-32 in the kernels), the host only writes
+    the bytes."""
+    data, off = ops.png_encode(rgba_dev).to_host()
     for n, ruta in enumerate(rutas):
         with open(ruta, "wb") as f:
-            f.write(host[n, :size].tobytes())
+            f.write(data[off[n]:off[n + 1]].tobytes())
 
 
 def guardar_cortes(paciente, images_dir, gt_masks_dir, num_cortes):

@@ -6,7 +6,7 @@ import torch
 
 from .. import ops
 from . import device
-from .utils import cargar_referencia_nifti, cargar_volumen, guardar_volumen
+from .utils import cargar_referencia_nifti, cargar_volumen, cargar_volumen_dispositivo, guardar_volumen
 
 
 def _u8_dev(vol, nombre):
@@ -27,7 +27,9 @@ def combinar_volumenes(axial_vol, coronal_vol, sagital_vol, umbral=2):
 
 
 def generar_consenso(axial_path, coronal_path, sagital_path, output_path, umbral=2):
-    axial_vol, coronal_vol, sagital_vol = cargar_volumen(axial_path), cargar_volumen(coronal_path), cargar_volumen(sagital_path)
+    """scripts/generar_consenso.py:112-127 without a host round trip: the three .nii.gz are inflated on the GPU, voted
+    there, and the consensus .nii.gz is deflated there (uint8 volume, affine of the axial file)."""
+    vols = [cargar_volumen_dispositivo(p, torch.uint8)[None] for p in (axial_path, coronal_path, sagital_path)]
     affine = cargar_referencia_nifti(axial_path)[1]
-    consenso = combinar_volumenes(axial_vol=axial_vol, coronal_vol=coronal_vol, sagital_vol=sagital_vol, umbral=umbral)
-    guardar_volumen(volumen=consenso, affine=affine, output_path=output_path)
+    consenso, _ = ops.consensus_eval(vols[0], vols[1], vols[2], None, umbral)
+    guardar_volumen(volumen=consenso[0], affine=affine, output_path=output_path)

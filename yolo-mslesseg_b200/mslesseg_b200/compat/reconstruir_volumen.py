@@ -9,6 +9,7 @@ import numpy as np
 import torch
 from PIL import Image
 
+from .. import codec as _codec
 from .. import ops
 from . import device
 from .utils import cargar_referencia_nifti, guardar_volumen, ruta_existente
@@ -72,10 +73,23 @@ def reconstruir_desde_cortes(cortes, indices, shape_original, plano) -> np.ndarr
 
 
 def reconstruir_volumen(pred_masks_dir, volumen_referencia, output_path, plano):
-    """Same signature and side effects as the reference (:199-213): writes a float32 NIfTI, returns the volume."""
+    """Same signature and side effects as the reference (:199-213): writes a float32 NIfTI, returns the volume.
+    The predicted-mask PNG FILES are uploaded as they are: inflate, scanline unfiltering, channel-0 selection and the
+    binarisation run on the GPU, the volume is stacked there and its .nii.gz is deflated there."""
     shape_original, affine = cargar_referencia_nifti(volumen_referencia)
     indices = extraer_indices_png(pred_masks_dir)
-    cortes = [cargar_mascara_png(Path(pred_masks_dir) / archivo) for archivo, _ in indices]
-    volumen = reconstruir_desde_cortes(cortes, [i for _, i in indices], shape_original, plano)
-    guardar_volumen(volumen, affine, output_path)
-    return volumen
+    archivos = []
+    for archivo, _ in indices:
+        ruta = Path(pred_masks_dir) / archivo
+        if not ruta_existente(ruta):
+            raise FileNotFoundError(f"No se encontró la imagen: {ruta}")
+        archivos.append(ruta.read_bytes())
+    X, Y, Z = (int(d) for d in shape_original)
+    n_p, rows, cols = ops.plane_dims(plano, X, Y, Z)
+    geos = [_codec.png_parse(b)[:2] for b in archivos]                       # (width, height) of every file
+    for (archivo, i), (w, h) in zip(indices, geos):
+        validar_corte(int(i), np.empty((h, w), dtype=np.uint8), shape_original, plano)   # index range + exact slice shape (:153-176)
+    st = _codec.png_decode_first_channel(archivos, device())                 # [n, rows, cols] uint8, slice orientation
+    vol = ops.recon(st, [0] * len(indices), [int(i) for _, i in indices], plano, 1, (X, Y, Z), dtype=torch.float32)
+    guardar_volumen(vol[0], affine, output_path)
+    return np.asfortranarray(vol[0].cpu().numpy().transpose(2, 1, 0))

@@ -5,13 +5,15 @@ import argparse
 import json
 import logging
 import os
+import struct
+import zlib
 from pathlib import Path
 
 import numpy as np
 import torch
 
 from .. import metrics as _M
-from .. import nifti as _nifti
+from .. import codec as _codec
 from .. import ops
 from . import device
 
@@ -23,10 +25,18 @@ def ruta_existente(path):
     return Path(path).exists()
 
 
+def cargar_volumen_dispositivo(vol_path, dtype=torch.float32):
+    """The volume of a .nii / .nii.gz as a device tensor [Z][Y][X] (float32, uint8 or float64): the FILE bytes are
+    uploaded and inflated / converted on the GPU (mslesseg_b200.codec).  uint8 / float32 raise ValueError when the file
+    holds values they cannot represent exactly."""
+    return _codec.nifti_load_device(vol_path, device(), dtype)[0]
+
+
 def cargar_volumen(vol_path):
-    """nib.load(vol_path).get_fdata(): float64 (X, Y, Z), Fortran order."""
+    """nib.load(vol_path).get_fdata(): float64 (X, Y, Z), Fortran order.  Decoded on the GPU, then copied back."""
     try:
-        return _nifti.load(vol_path, np.float64)[0]
+        v = cargar_volumen_dispositivo(vol_path, torch.float64)
+        return np.asfortranarray(v.cpu().numpy().transpose(2, 1, 0))
     except Exception as e:
         logger.error(f"❌ Error al cargar el volumen desde {vol_path}: {e}")
         raise
@@ -36,14 +46,31 @@ def cargar_referencia_nifti(referencia_path):
     if not ruta_existente(referencia_path):
         raise FileNotFoundError(f"Archivo no encontrado: {referencia_path}")
     try:
-        return _nifti.shape_affine(referencia_path)
-    except _nifti.ImageFileError as e:
+        return _codec.nifti_read_header(referencia_path)
+    except (_codec.CodecError, zlib.error, OSError, struct.error) as e:
         raise ValueError(f"Archivo no válido: {referencia_path}") from e
 
 
+_TORCH_DT = {np.dtype(np.float32): torch.float32, np.dtype(np.uint8): torch.uint8, np.dtype(np.float64): torch.float64,
+             np.dtype(np.int16): torch.int16, np.dtype(np.int32): torch.int32, np.dtype(np.int8): torch.int8}
+
+
 def guardar_volumen(volumen, affine, output_path):
+    """nib.save(nib.Nifti1Image(volumen, affine), output_path): the .nii.gz is deflated on the GPU (64 KB gzip members,
+    readable by any gzip / nibabel); `volumen` may be a NumPy array (X, Y, Z) or a device tensor [Z][Y][X]."""
     try:
-        _nifti.save(volumen, affine, output_path)
+        if isinstance(volumen, torch.Tensor):
+            dev = volumen
+        else:
+            a = np.asarray(volumen)
+            if a.dtype == np.bool_:
+                a = a.astype(np.uint8)
+            if a.dtype not in _TORCH_DT:
+                raise ValueError(f"no se puede guardar un volumen de tipo {a.dtype} en NIfTI-1")
+            if a.ndim != 3:
+                raise ValueError(f"se esperaba un volumen 3D, forma {a.shape}")
+            dev = torch.from_numpy(np.ascontiguousarray(a.transpose(2, 1, 0))).to(device())
+        _codec.nifti_save_device(dev, affine, output_path)
     except Exception as e:
         logger.error(f"❌ Error al guardar el volumen en {output_path}: {e}")
         raise
@@ -51,7 +78,7 @@ def guardar_volumen(volumen, affine, output_path):
 
 def reconstruccion_valida(pred_vol_path, gt_vol_path):
     """Shape equality of the two volumes (utils/utils.py:183-194); only the headers are read."""
-    ps, gs = _nifti.shape_affine(pred_vol_path)[0], _nifti.shape_affine(gt_vol_path)[0]
+    ps, gs = _codec.nifti_read_header(pred_vol_path)[0], _codec.nifti_read_header(gt_vol_path)[0]
     if ps != gs:
         logger.warning(f"⚠️ Dimensiones distintas: {ps} vs {gs}")
         return False

@@ -2,9 +2,10 @@
 
 Host-side file I/O is out of scope as a kernel but the drop-in shims need
 `nib.load(path).get_fdata()`, `.shape`, `.affine` and `nib.save(Nifti1Image(vol, affine), path)`
-(reference utils/utils.py:153-181, utils/Paciente.py:168,179).  nibabel is used when it is importable;
-otherwise this module covers what the MSLesSeg files need: float32 / uint8 / int16 / float64 data,
-little- or big-endian, sform or qform-less affine, scl_slope / scl_inter.
+(reference utils/utils.py:153-181, utils/Paciente.py:168,179).  The shims themselves decode and encode the files on
+the GPU (mslesseg_b200.codec); this host-side reader / writer (Python gzip) is what tests and tools use to make and
+check such files without a GPU: float32 / uint8 / int16 / float64 data, little- or big-endian, sform or qform
+affine, scl_slope / scl_inter with nibabel's rule (slope 0 or non-finite = no scaling at all).
 """
 from __future__ import annotations
 
@@ -75,9 +76,9 @@ def load(path, dtype=None):
     shape, affine, dt, off, raw, slope, inter = read_header(path)
     n = int(np.prod(shape))
     arr = np.frombuffer(raw, dtype=dt, count=n, offset=off).reshape(shape, order="F")
-    scaled = (slope not in (0.0, 1.0) and np.isfinite(slope)) or (inter != 0.0 and np.isfinite(inter))
+    scaled = bool(np.isfinite(slope) and slope != 0.0 and np.isfinite(inter) and (slope != 1.0 or inter != 0.0))
     if scaled:
-        arr = arr.astype(np.float64) * (slope if slope not in (0.0,) and np.isfinite(slope) else 1.0) + inter
+        arr = arr.astype(np.float64) * slope + inter
     if dtype is not None:
         arr = arr.astype(dtype)
     elif not scaled:
