@@ -99,6 +99,13 @@ size_t msl_workspace_bytes(int op, int nvol, int X, int Y, int Z);
 int msl_lesion_slices(const void* gt, int dtype, int nvol, int X, int Y, int Z,
                       uint8_t* any_ax, uint8_t* any_co, uint8_t* any_sa, msl_stream_t stream);
 
+/* ---- E1 statistics: per-slice intensity range of the three planes -------------------------------------
+ * The min / ptp that normalizar_a_uint8 (utils/utils.py:400-405) takes per slice, for every slice of every plane in one
+ * pass over the volume; also what calcular_rango_global (extras/generar_gif_predicciones.py:141-148: minimum and maximum
+ * over a list of slices) reduces.  vol: float32 [nvol][Z][Y][X]; ranges: float32 [nvol][Z + Y + X][2] = {min, max},
+ * rows [0, Z) axial, [Z, Z+Y) coronal, [Z+Y, Z+Y+X) sagital.  X <= 256. */
+int msl_slice_ranges(const float* vol, int nvol, int X, int Y, int Z, float* ranges, msl_stream_t stream);
+
 /* ---- E1-E8: enhance a list of slices of resident volumes ------------------------------------
  * Replaces, per slice, Paciente.obtener_corte_imagen (utils/Paciente.py:216-222) ->
  * aplicar_mejora (:195-210) -> <HE|CLAHE|GC|LT>.aplicar (utils/mejora_imagen.py) incl.
@@ -204,6 +211,21 @@ int msl_png_unfilter(uint8_t* raw, const uint64_t* raw_off, int n, int H, int W,
                      uint8_t* out, uint32_t* status, msl_stream_t stream);
 int msl_nifti_convert(const uint8_t* payload, int datatype, uint64_t nvox, double slope, double inter, int scaled,
                       float* out_f32, uint8_t* out_u8, double* out_f64, uint64_t* inexact, msl_stream_t stream);
+
+/* ---- E9: external contours of binary masks (YOLO label polygons) ----------------------------
+ * Replaces the contour extraction behind anotar_mascaras (scripts/extraer_dataset.py:215-227): ultralytics'
+ * convert_segment_masks_to_yolo_seg runs cv2.findContours((mask == value), RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) on every
+ * mask PNG and writes one "class x1 y1 x2 y2 ..." line per contour with at least 3 points.
+ * masks: uint8 [n][H][W].  Foreground = (byte == value), or any non-zero byte when value == 0.  Per mask the contours come
+ * out in OpenCV's order with OpenCV's points (x, y as int16), back to back in points[i][...]:
+ *   counts      uint32 [n][4]  = {contours stored, points stored, overflow flags (1: > max_contours, 2: > max_points),
+ *                                 contours found}
+ *   contour_len uint32 [n][max_contours]  points of each contour
+ *   points      int16  [n][max_points][2]
+ * The normalisation (x / width, y / height, 6 decimals) and the text stay on the host.  Masks up to ~45,000 pixels
+ * ((H + 2) * (W + 2) * 5 bytes of shared memory). */
+int msl_mask_contours(const uint8_t* masks, int n, int H, int W, int value, int max_contours, int max_points,
+                      uint32_t* counts, uint32_t* contour_len, int16_t* points, msl_stream_t stream);
 
 /* ---- host hand-off helpers: copy only the non-zero box of a result ------------------------------
  * Skull-stripped volumes are two thirds background and predicted masks ~99 % zeros, and the device-to-host copy of the

@@ -575,3 +575,20 @@ def test_no_cpu_fallback(ops, torch_mod):
     torch = torch_mod
     with pytest.raises(TypeError):
         ops.enhance_images(torch.zeros((1, 8, 8)), "GC")
+
+
+def test_slice_ranges_equal_numpy_min_max(cuda_device):
+    """msl_slice_ranges: the per-slice (min, max) of the three planes - the statistics of normalizar_a_uint8
+    (utils/utils.py:400-405) and the input of calcular_rango_global (extras/generar_gif_predicciones.py:141-148)."""
+    import torch
+    from mslesseg_b200 import ops, metrics as M
+    rng = np.random.default_rng(21)
+    for shape in ((2, 182, 218, 182), (3, 17, 23, 29)):
+        v = (rng.standard_normal(shape) * 300).astype(np.float32)
+        v[0, :, :, :3] = 0
+        r = ops.slice_ranges(torch.from_numpy(v).to(cuda_device))
+        for plano, axis in (("axial", (2, 3)), ("coronal", (1, 3)), ("sagital", (1, 2))):
+            got = r[plano].cpu().numpy()
+            assert np.array_equal(got[..., 0], v.min(axis=axis)) and np.array_equal(got[..., 1], v.max(axis=axis))
+        g = r["axial"][1].cpu().numpy()
+        assert M.calcular_rango_global(g, [0, 5, 9]) == (min(v[1, i].min() for i in (0, 5, 9)), max(v[1, i].max() for i in (0, 5, 9)))

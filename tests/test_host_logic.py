@@ -129,3 +129,21 @@ def test_fold_logic_against_reference(golden):
     assert M.ventana_central(list(range(50, 151)), 20) == list(range(90, 110))
     assert M.ventana_central([1, 2, 3], 20) == [1, 2, 3] and M.ventana_central([1, 2, 3], None) == [1, 2, 3]
     assert len(d["usar20"]) == 20
+
+
+def test_iou_and_rango_global():
+    from mslesseg_b200 import metrics as M
+    assert M.iou_desde_conteos(3, 1, 2) == 0.5
+    assert M.iou_desde_conteos(0, 0, 0) == 0.0
+    assert M.iou_desde_conteos(7, 0, 0) == 1.0
+    m = M.metricas_desde_conteos(30, 10, 20, 940)
+    assert "IoU" not in m                                   # reference JSONs stay identical by default
+    m2 = M.metricas_desde_conteos(30, 10, 20, 940, con_iou=True)
+    assert m2["IoU"] == 0.5 and {k: v for k, v in m2.items() if k != "IoU"} == m
+    # Jaccard and Dice of the same counts: J = D / (2 - D) up to the rounding of both
+    assert abs(m2["IoU"] - m2["DSC"] / (2 - m2["DSC"])) < 2e-3
+    r = np.array([[0.0, 10.0], [-3.0, 4.0], [1.0, 99.0]])
+    assert M.calcular_rango_global(r) == (-3.0, 99.0)
+    assert M.calcular_rango_global(r, [0, 2]) == (0.0, 99.0)
+    with pytest.raises(ValueError):
+        M.calcular_rango_global(r, [])

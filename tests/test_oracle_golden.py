@@ -248,3 +248,20 @@ def test_png_container_oracle_decodes():
         cv2 = pytest.importorskip("cv2")
         d = cv2.imdecode(np.frombuffer(b, np.uint8), cv2.IMREAD_UNCHANGED)
         assert np.array_equal(d[..., [2, 1, 0, 3]] if a.ndim == 3 else d, a)
+
+
+def test_label_goldens_reproduce_with_installed_cv2():
+    """The frozen label text digests of the demo masks (oracle/make_golden_labels.py) are reproduced by the restated
+    ultralytics converter on this machine's cv2 - so a cv2 upgrade that changes findContours is noticed on the CPU."""
+    import json
+    pytest.importorskip("cv2")
+    from conftest import GOLDEN_DIR
+    from oracle import ref_stubs
+    z = np.load(GOLDEN_DIR / "demo_label_masks.npz")
+    gold = json.loads((GOLDEN_DIR / "demo_labels_v1.json").read_text())
+    for key in ("P18_axial", "P39_sagital"):
+        shape = tuple(int(d) for d in z[key + "_shape"])
+        masks = np.unpackbits(z[key + "_bits"])[:int(np.prod(shape))].reshape(shape)
+        for i, m in enumerate(masks):
+            text = "".join(ln + "\n" for ln in ref_stubs.yolo_seg_lines(m, 1))
+            assert hashlib.sha256(text.encode()).hexdigest() == gold[key]["sha"][i]

@@ -120,6 +120,21 @@ int msl_lesion_slices(const void* gt, int dtype, int nvol, int X, int Y, int Z,
     return launch_lesion_flags(gt, dtype, nvol, X, Y, Z, any_ax, any_co, any_sa, (cudaStream_t)stream);
 }
 
+int msl_slice_ranges(const float* vol, int nvol, int X, int Y, int Z, float* ranges, msl_stream_t stream_) {
+    MSL_REQUIRE(vol && ranges, "NULL pointer");
+    MSL_REQUIRE(nvol > 0 && X > 0 && Y > 0 && Z > 0, "non-positive size");
+    MSL_REQUIRE(nvol <= 65535, "at most 65535 volumes per call");
+    if (X > 256) { set_error("msl_slice_ranges supports X <= 256 (got %d)", X); return MSL_ERR_UNSUPPORTED; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    unsigned* stats = reinterpret_cast<unsigned*>(ranges);
+    const size_t n = (size_t)nvol * (X + Y + Z);
+    int rc = launch_init_stats(stats, n, stream);
+    if (rc) return rc;
+    rc = launch_plane_stats_f32(vol, nvol, X, Y, Z, stats, stream);
+    if (rc) return rc;
+    return launch_stats_keys_to_float(stats, n * 2, stream);
+}
+
 int msl_enhance_slices(const void* vol, int dtype, int nvol, int X, int Y, int Z, int mejora, int plano,
                        const int32_t* vol_of_slice, const int32_t* idx_of_slice, int nslices,
                        uint8_t* out, size_t slice_pitch_bytes, int layout, const uint8_t* tables, msl_stream_t stream) {
@@ -357,6 +372,16 @@ int msl_nifti_convert(const uint8_t* payload, int datatype, uint64_t nvox, doubl
     }
     return launch_nifti_convert(payload, datatype, nvox, slope, inter, scaled, out_f32, out_u8, out_f64,
                                 reinterpret_cast<unsigned long long*>(inexact), (cudaStream_t)stream);
+}
+
+int msl_mask_contours(const uint8_t* masks, int n, int H, int W, int value, int max_contours, int max_points, uint32_t* counts,
+                      uint32_t* contour_len, int16_t* points, msl_stream_t stream) {
+    MSL_REQUIRE(n >= 0 && H > 0 && W > 0, "non-positive size");
+    MSL_REQUIRE(value >= 0 && value <= 255, "value %d outside 0..255", value);
+    MSL_REQUIRE(max_contours > 0 && max_points > 0, "non-positive capacity");
+    if (n == 0) return MSL_OK;
+    MSL_REQUIRE(masks && counts && contour_len && points, "NULL pointer");
+    return launch_contours(masks, n, H, W, value, max_contours, max_points, counts, contour_len, points, (cudaStream_t)stream);
 }
 
 int msl_nonzero_flags(const uint8_t* stack, int nvol, int A, int B, int C, uint8_t* any_a, uint8_t* any_b, msl_stream_t stream) {

@@ -34,7 +34,8 @@ enum KernelKind {
     K_PNG_UNFILTER = 30,
     K_NIFTI_CONVERT = 31,
     K_CHECKSUM = 32,
-    K_NKIND = 33
+    K_CONTOURS = 33,
+    K_NKIND = 34
 };
 
 // RAII: counts the launch and, when profiling is enabled, brackets it with CUDA events on `stream`.
@@ -79,6 +80,7 @@ int launch_enhance_slices(EnhParams p, int dtype, int nslices, cudaStream_t stre
 // stats: [nvol][Z + Y + X][2] = {min key, max key}; must be pre-initialised by init_stats.
 int launch_init_stats(unsigned* stats, size_t nslices_total, cudaStream_t stream);
 int launch_plane_stats_f32(const float* vol, int nvol, int X, int Y, int Z, unsigned* stats, cudaStream_t stream);
+int launch_stats_keys_to_float(unsigned* stats, size_t n, cudaStream_t stream);    // order-preserving keys -> float bits, in place
 
 // E0: any(voxel > 0) per slice for the three planes.
 int launch_lesion_flags(const void* gt, int dtype, int nvol, int X, int Y, int Z,
@@ -132,6 +134,10 @@ int launch_png_unfilter(uint8_t* raw, const unsigned long long* raw_off, int n, 
                         cudaStream_t stream);
 int launch_nifti_convert(const uint8_t* payload, int datatype, unsigned long long nvox, double slope, double inter, int scaled,
                          float* out_f32, uint8_t* out_u8, double* out_f64, unsigned long long* inexact, cudaStream_t stream);
+// msl_contours.cu: external contours of binary masks (cv2.findContours RETR_EXTERNAL / CHAIN_APPROX_SIMPLE)
+size_t contours_smem_bytes(int H, int W);
+int launch_contours(const uint8_t* masks, int n, int H, int W, int value, int max_contours, int max_points, uint32_t* counts,
+                    uint32_t* contour_len, short* points, cudaStream_t stream);
 int launch_nonzero_flags(const uint8_t* stack, int nvol, int A, int B, int C, uint8_t* any_a, uint8_t* any_b, cudaStream_t stream);
 int launch_slice_counts(const uint8_t* gt, const uint8_t* pred, int nvol, int X, int Y, int Z, long long* counts, cudaStream_t stream);
 int launch_consensus_eval(const uint8_t* ax, const uint8_t* co, const uint8_t* sa, const uint8_t* gt,

@@ -39,6 +39,7 @@ _SIGNATURES = {
     "msl_last_error": (C.c_char_p, []),
     "msl_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i, _i]),
     "msl_lesion_slices": (C.c_int, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "msl_slice_ranges": (C.c_int, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "msl_enhance_slices": (C.c_int, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _sz, _i, _vp, _vp]),
     "msl_enhance_images": (C.c_int, [_vp, _i, _i, _i, _i, _sz, _i, _vp, _sz, _i, _vp, _vp]),
     "msl_enhance_volumes": (C.c_int, [_vp, _i, _i, _i, _i, C.POINTER(C.c_void_p), _vp, _vp, _sz, _vp]),
@@ -51,6 +52,7 @@ _SIGNATURES = {
     "msl_inflate": (C.c_int, [_vp, _sz, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "msl_png_unfilter": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "msl_nifti_convert": (C.c_int, [_vp, _i, C.c_uint64, C.c_double, C.c_double, _i, _vp, _vp, _vp, _vp, _vp]),
+    "msl_mask_contours": (C.c_int, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "msl_nonzero_flags": (C.c_int, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "msl_copy_box_d2h": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "msl_copy_boxes_d2h": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),

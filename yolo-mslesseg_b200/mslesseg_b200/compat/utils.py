@@ -162,6 +162,17 @@ def verificar_grises(imagen):
     return imagen
 
 
+def normalizar_mascara_binaria(mask_path):
+    """utils/utils.py:387-393: cv2.imread(GRAYSCALE) -> (mask > 0) -> cv2.imwrite, the file rewritten in place as an 8-bit
+    gray PNG with values {0, 1}.  Decode, threshold and encode run on the GPU (the gray value of the gray-colormapped RGBA
+    files guardar_cortes writes is their first channel)."""
+    from pathlib import Path as _P
+    px = _codec.png_decode_first_channel([_P(mask_path).read_bytes()], device())
+    data, off = ops.png_encode((px > 0).to(torch.uint8)).to_host()
+    with open(mask_path, "wb") as f:
+        f.write(data[:int(off[1])].tobytes())
+
+
 # ---- metrics (utils/utils.py:455-495) ---------------------------------------------------------------
 def _as_mask_u8(a, nombre):
     a = np.asarray(a)

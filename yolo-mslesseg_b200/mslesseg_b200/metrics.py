@@ -28,9 +28,29 @@ def auc_binario(tp: int, fp: int, fn: int, tn: int) -> float:
     return float((np.diff(fpr) * (tpr[1:] + tpr[:-1]) / 2.0).sum())
 
 
-def metricas_desde_conteos(tp: int, fp: int, fn: int, tn: int) -> dict:
+def iou_desde_conteos(tp: int, fp: int, fn: int) -> float:
+    """Jaccard index tp / (tp + fp + fn) of two binary arrays from their counts.  NOT a reference metric (the reference
+    computes DSC / AUC / precision / recall only, scripts/eval.py:121-126); BASELINE.json's north_star names it, so it is
+    offered with the reference's conventions: + 1e-8 in the denominator, float64, np.round(., 3)."""
+    tp64, fp64, fn64 = np.int64(int(tp)), np.int64(int(fp)), np.int64(int(fn))
+    return float(np.round(tp64 / (tp64 + fp64 + fn64 + 1e-8), 3))
+
+
+def calcular_rango_global(rangos, cortes=None):
+    """extras/generar_gif_predicciones.py:141-148 on per-slice (min, max) pairs [n, 2] (ops.slice_ranges of one patient
+    and plane): (global minimum, global maximum) over the listed slices (default: all)."""
+    r = np.asarray(rangos)
+    if cortes is not None:
+        r = r[list(cortes)]
+    if r.shape[0] == 0:
+        raise ValueError("min() arg is an empty sequence")
+    return r[:, 0].min(), r[:, 1].max()
+
+
+def metricas_desde_conteos(tp: int, fp: int, fn: int, tn: int, con_iou: bool = False) -> dict:
     """generar_diccionario_metricas (scripts/eval.py:115-128) for binary volumes.
-    sum(gt*pred) = tp, sum(gt) = tp+fn, sum(pred) = tp+fp are exact in float64."""
+    sum(gt*pred) = tp, sum(gt) = tp+fn, sum(pred) = tp+fp are exact in float64.
+    con_iou=True adds an "IoU" key (iou_desde_conteos); off by default so that the JSON files equal the reference's."""
     tp, fp, fn, tn = int(tp), int(fp), int(fn), int(tn)
     tp64, fp64, fn64 = np.int64(tp), np.int64(fp), np.int64(fn)
     dsc = (2.0 * np.float64(tp)) / (np.float64(tp + fn) + np.float64(tp + fp) + 1e-8)
@@ -41,12 +61,15 @@ def metricas_desde_conteos(tp: int, fp: int, fn: int, tn: int) -> dict:
         auc = float("nan")
     else:
         auc = float(np.round(auc_binario(tp, fp, fn, tn), 3))
-    return {
+    out = {
         "DSC": float(np.round(dsc, 3)),
         "AUC": auc,
         "Precision": float(np.round(prec, 3)),
         "Recall": float(np.round(rec, 3)),
     }
+    if con_iou:
+        out["IoU"] = iou_desde_conteos(tp, fp, fn)
+    return out
 
 
 def dsc_desde_conteos(tp: int, fp: int, fn: int) -> float:

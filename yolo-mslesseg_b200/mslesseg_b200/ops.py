@@ -103,6 +103,18 @@ def lesion_slices(gt: torch.Tensor):
 
 
 # ------------------------------------------------------------------------------------ E1-E8
+def slice_ranges(vol: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """{plano: float32 [nvol, n_plane, 2]} = (min, max) of every slice of the three planes in one pass over the float32
+    volumes [nvol, Z, Y, X] (the statistics of normalizar_a_uint8, reference utils/utils.py:400-405)."""
+    _need_cuda(vol, "vol")
+    if vol.dtype != torch.float32 or vol.dim() != 4:
+        raise ValueError("vol must be float32 [nvol, Z, Y, X]")
+    nvol, Z, Y, X = (int(d) for d in vol.shape)
+    out = torch.empty((nvol, Z + Y + X, 2), dtype=torch.float32, device=vol.device)
+    L.check(L.load().msl_slice_ranges(_ptr(vol), nvol, X, Y, Z, _ptr(out), _stream()))
+    return {"axial": out[:, :Z], "coronal": out[:, Z:Z + Y], "sagital": out[:, Z + Y:]}
+
+
 def enhance_slices(vol: torch.Tensor, mejora: Optional[str], plano: str, vol_of_slice=None, idx_of_slice=None,
                    layout: str = "G", out: Optional[torch.Tensor] = None, lut_out: str = "gray") -> torch.Tensor:
     """Enhanced slices of resident volumes.  vol: [nvol, Z, Y, X] float32 (normalised per slice like
@@ -417,6 +429,46 @@ def png_encode(pixels: torch.Tensor, out: Optional[torch.Tensor] = None, workspa
     off = torch.zeros(n + 1, dtype=torch.int64, device=pixels.device)
     L.check(lib.msl_png_encode(_ptr(pixels), n, H, W, ch, _ptr(out), out.numel(), _ptr(off), _ptr(workspace), workspace.numel(), _stream()))
     return PackedStreams(out, off)
+
+
+# ------------------------------------------------------------------------------------ label polygons
+def mask_contours(masks: torch.Tensor, value: int = 0, max_contours: int = 256, max_points: int = 8192):
+    """External contours of binary masks uint8 [n, H, W], as cv2.findContours(mask == value (or mask != 0 when value is
+    0), RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) returns them (reference scripts/extraer_dataset.py:215-227 via ultralytics).
+    Returns a list (one entry per mask) of lists of int32 arrays [npoints, 2] (x, y) in OpenCV's order.  Capacities are
+    grown and the call repeated when a mask holds more contours / points than asked for."""
+    _need_cuda(masks, "masks")
+    if masks.dtype != torch.uint8 or masks.dim() != 3:
+        raise ValueError("masks must be uint8 [n, H, W]")
+    masks = masks.contiguous()
+    n, H, W = (int(d) for d in masks.shape)
+    if n == 0:
+        return []
+    while True:
+        counts = torch.empty((n, 4), dtype=torch.int32, device=masks.device)
+        clen = torch.empty((n, max_contours), dtype=torch.int32, device=masks.device)
+        pts = torch.empty((n, max_points, 2), dtype=torch.int16, device=masks.device)
+        L.check(L.load().msl_mask_contours(_ptr(masks), n, H, W, int(value), max_contours, max_points, _ptr(counts), _ptr(clen),
+                                           _ptr(pts), _stream()))
+        c = counts.cpu().numpy()
+        if (c[:, 2] & 1).any():
+            max_contours = int(c[:, 3].max()) + 1
+            continue
+        if (c[:, 2] & 2).any():
+            max_points *= 4
+            continue
+        break
+    ncmax, npmax = int(c[:, 0].max()), int(c[:, 1].max())
+    lens = clen[:, :max(ncmax, 1)].cpu().numpy()
+    pp = pts[:, :max(npmax, 1)].cpu().numpy().astype(np.int32)
+    out = []
+    for i in range(n):
+        o, cs = 0, []
+        for k in range(int(c[i, 0])):
+            cs.append(pp[i, o:o + int(lens[i, k])])
+            o += int(lens[i, k])
+        out.append(cs)
+    return out
 
 
 # ------------------------------------------------------------------------------------ host hand-off
