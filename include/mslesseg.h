@@ -171,6 +171,11 @@ int msl_png_pack(const uint8_t* pixels, int n, int H, int W, int channels,
  * {container bytes, raw bytes, Adler-32 / CRC-32 of the raw bytes, 0}.  ws: msl_deflate_workspace_bytes(...), 16-byte aligned.
  *
  * msl_deflate_chunks: `total_len` bytes at src cut into n = ceil(total_len / chunk_len) streams (chunk_len < 16 MB).
+ * msl_deflate_files : nfiles files at once, file f = prefix f (prefix_len bytes at prefix + f * prefix_pitch; pitch 0 = one
+ *                     prefix for all: a NIfTI header) followed by body f (body_len bytes at bodies + f * body_pitch), each
+ *                     cut into ceil(file bytes / chunk_len) streams; streams are numbered file-major.  With
+ *                     expand_u8_to_f32 the body is a uint8 mask and the file holds it as float32 0.0f / 1.0f (what
+ *                     reconstruir_volumen saves, scripts/reconstruir_volumen.py:202) without that volume ever existing.
  * msl_png_encode    : pixels uint8 [n][H][W][channels] (channels 1, 2, 3 or 4) -> n PNG files. */
 #define MSL_Z_RAW  0
 #define MSL_Z_ZLIB 1
@@ -181,6 +186,11 @@ size_t msl_deflate_workspace_bytes(int n, int container, size_t raw_len_per_stre
 int msl_deflate_chunks(const uint8_t* src, size_t total_len, size_t chunk_len, int container, int dist2,
                        uint8_t* out, size_t out_cap, uint64_t* out_off, uint32_t* out_meta,
                        void* ws, size_t ws_bytes, msl_stream_t stream);
+int msl_deflate_files(const uint8_t* bodies, int nfiles, size_t body_pitch, size_t body_len,
+                      const uint8_t* prefix, size_t prefix_pitch, size_t prefix_len, int expand_u8_to_f32,
+                      size_t chunk_len, int container, int dist2,
+                      uint8_t* out, size_t out_cap, uint64_t* out_off, uint32_t* out_meta,
+                      void* ws, size_t ws_bytes, msl_stream_t stream);
 int msl_png_encode(const uint8_t* pixels, int n, int H, int W, int channels,
                    uint8_t* out, size_t out_cap, uint64_t* out_off,
                    void* ws, size_t ws_bytes, msl_stream_t stream);

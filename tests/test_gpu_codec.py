@@ -220,3 +220,32 @@ def test_nifti_gz_round_trip_on_device(ops, codec, cuda_device, tmp_path):
     # values a uint8 volume cannot hold are refused
     with pytest.raises(codec.CodecError):
         codec.nifti_load_device(p1, cuda_device, torch.uint8)
+
+
+def test_deflate_files_prefix_expand_and_index(ops, codec, cuda_device):
+    """Several files in one launch: shared header prefix + body per file, uint8 masks stored as float32, and the index
+    member that lets a reader split the file without hopping from member to member."""
+    import torch
+    rng = np.random.default_rng(3)
+    masks = (rng.random((3, 20, 30, 40)) > 0.98).astype(np.uint8)
+    masks[1] = 0
+    aff = np.diag([1.0, 1.0, 1.0, 1.0])
+    ps = codec.nifti_gz_device(torch.from_numpy(masks).to(cuda_device), aff, como_float32=True)
+    assert ps.streams_per_file == -(-(352 + masks[0].size * 4) // 65536)
+    for f in range(3):
+        blob = codec.nifti_gz_bytes(ps, f)
+        raw = gzip.decompress(blob)
+        assert len(raw) == 352 + masks[f].size * 4
+        assert raw[:352] == codec.nifti_header_bytes((40, 30, 20), np.float32, aff)
+        assert np.array_equal(np.frombuffer(raw, "<f4", offset=352), masks[f].reshape(-1).astype(np.float32))
+        tab = codec.gzip_member_table(blob)
+        assert tab is not None and len(tab) == ps.streams_per_file and int(tab[:, 2].sum()) == len(raw)
+    # plain float32 volumes, per-file prefixes
+    vols = np.round(rng.uniform(0, 900, (2, 9, 11, 13))).astype(np.float32)
+    pref = np.stack([np.frombuffer(codec.nifti_header_bytes((13, 11, 9), np.float32, aff * (k + 1)), np.uint8) for k in range(2)])
+    ps = ops.deflate_files(torch.from_numpy(vols).to(cuda_device), prefix=torch.from_numpy(pref.copy()).to(cuda_device), chunk_len=1000, dist2=4)
+    data, off = ps.to_host()
+    spv = ps.streams_per_file
+    for f in range(2):
+        raw = gzip.decompress(data[off[f * spv]:off[(f + 1) * spv]].tobytes())
+        assert raw == pref[f].tobytes() + vols[f].tobytes()

@@ -320,13 +320,24 @@ size_t msl_deflate_workspace_bytes(int n, int container, size_t raw) {
 
 int msl_deflate_chunks(const uint8_t* src, size_t total_len, size_t chunk_len, int container, int dist2, uint8_t* out, size_t out_cap,
                        uint64_t* out_off, uint32_t* out_meta, void* ws, size_t ws_bytes, msl_stream_t stream) {
+    return msl_deflate_files(src, 1, total_len, total_len, nullptr, 0, 0, 0, chunk_len, container, dist2, out, out_cap, out_off, out_meta,
+                             ws, ws_bytes, stream);
+}
+
+int msl_deflate_files(const uint8_t* bodies, int nfiles, size_t body_pitch, size_t body_len, const uint8_t* prefix, size_t prefix_pitch,
+                      size_t prefix_len, int expand_u8_to_f32, size_t chunk_len, int container, int dist2, uint8_t* out, size_t out_cap,
+                      uint64_t* out_off, uint32_t* out_meta, void* ws, size_t ws_bytes, msl_stream_t stream) {
     MSL_REQUIRE(container >= MSL_Z_RAW && container <= MSL_Z_GZIP, "container %d no válido (MSL_Z_RAW / ZLIB / GZIP)", container);
-    MSL_REQUIRE(chunk_len > 0, "chunk_len must be positive");
+    MSL_REQUIRE(chunk_len > 0 && nfiles > 0, "chunk_len and nfiles must be positive");
     MSL_REQUIRE(out && out_off, "NULL out / out_off");
-    MSL_REQUIRE(src || total_len == 0, "NULL src");
-    const size_t n = total_len == 0 ? 1 : (total_len + chunk_len - 1) / chunk_len;
-    MSL_REQUIRE(n <= 0x7fffffff, "too many chunks");
-    return launch_deflate_pack(src, (int)n, chunk_len, chunk_len, total_len, 0, 0, 0, 0, container, dist2, out, out_cap,
+    MSL_REQUIRE(bodies || body_len == 0, "NULL bodies");
+    MSL_REQUIRE(prefix || prefix_len == 0, "NULL prefix");
+    MSL_REQUIRE(nfiles == 1 || body_pitch >= body_len, "body pitch smaller than a body");
+    const size_t total = prefix_len + body_len * (expand_u8_to_f32 ? 4 : 1);
+    const size_t spv = total == 0 ? 1 : (total + chunk_len - 1) / chunk_len;
+    MSL_REQUIRE(spv * (size_t)nfiles <= 0x7fffffff, "too many chunks");
+    return launch_deflate_pack(bodies, (int)(spv * nfiles), body_pitch, chunk_len, total, 0, 0, 0, 0, container, dist2,
+                               prefix_len ? prefix : nullptr, prefix_pitch, prefix_len, expand_u8_to_f32 ? 1 : 0, out, out_cap,
                                reinterpret_cast<unsigned long long*>(out_off), out_meta, ws, ws_bytes, (cudaStream_t)stream);
 }
 
@@ -339,7 +350,8 @@ int msl_png_encode(const uint8_t* pixels, int n, int H, int W, int channels, uin
     MSL_REQUIRE(pixels && out, "NULL pointer");
     const size_t rb = (size_t)W * channels;
     MSL_REQUIRE(rb < (1u << 24), "scanline too long");
-    return launch_deflate_pack(pixels, n, (size_t)H * rb, 0, 0, H, (int)rb, W, channels, MSL_Z_PNG, channels > 1 ? channels : 0, out, out_cap,
+    return launch_deflate_pack(pixels, n, (size_t)H * rb, 0, 0, H, (int)rb, W, channels, MSL_Z_PNG, channels > 1 ? channels : 0, nullptr, 0, 0, 0,
+                               out, out_cap,
                                reinterpret_cast<unsigned long long*>(out_off), nullptr, ws, ws_bytes, (cudaStream_t)stream);
 }
 

@@ -50,9 +50,14 @@ __host__ __device__ inline uint32_t gf_xpow8(unsigned long long n) {
 
 struct ZArgs {
     const uint8_t* src;
-    size_t src_pitch;          // bytes between the sources of consecutive streams
-    unsigned long long total;  // plain mode: bytes of the whole buffer (the last chunk may be short)
+    size_t src_pitch;          // image mode: bytes between consecutive images; plain mode: bytes between consecutive BODIES
+    unsigned long long total;  // plain mode: raw bytes of one source = prefix + body (x 4 when expanding); its last chunk may be short
     unsigned chunk;            // plain mode: raw bytes per stream
+    unsigned spv;              // plain mode: streams per source (ceil(total / chunk)); stream s = source s / spv, chunk s % spv
+    const uint8_t* prefix;     // plain mode: bytes in front of every body (a file header), or NULL
+    size_t prefix_pitch;       // bytes between the prefixes of consecutive sources (0: one prefix for all)
+    unsigned prefix_len;
+    int expand;                // plain mode: the body is uint8 {0, != 0}; the raw stream holds it as float32 0.0f / 1.0f
     int rows, row_bytes;       // image mode (rows > 0): `rows` scanlines of row_bytes bytes, each prefixed by filter byte 0
     int img_w, img_ch;         // PNG IHDR
     int container;             // MSL_Z_*
@@ -180,11 +185,16 @@ __global__ void __launch_bounds__(kZThreads) deflate_kernel(const ZArgs a) {
     const unsigned rl = image ? (unsigned)a.row_bytes + 1u : 0u;
     unsigned n;                                            // raw bytes of this stream
     if (image) n = (unsigned)a.rows * rl;
-    else {
-        const unsigned long long b0 = (unsigned long long)s * a.chunk;
-        n = b0 >= a.total ? 0u : (unsigned)min((unsigned long long)a.chunk, a.total - b0);
+    unsigned long long r0 = 0;                            // plain mode: raw offset of this stream inside its source
+    unsigned vsrc = s;
+    if (!image) {
+        vsrc = s / a.spv;
+        r0 = (unsigned long long)(s - vsrc * a.spv) * a.chunk;
+        n = r0 >= a.total ? 0u : (unsigned)min((unsigned long long)a.chunk, a.total - r0);
     }
-    const uint8_t* src = a.src + (size_t)s * a.src_pitch;
+    const uint8_t* src = a.src + (size_t)vsrc * a.src_pitch;
+    const uint8_t* pfx = a.prefix ? a.prefix + (size_t)vsrc * a.prefix_pitch : nullptr;
+    const unsigned plen = a.prefix ? a.prefix_len : 0u;
     uint8_t* slot = a.slots + (size_t)s * a.slot_pitch;
     const unsigned hdr = hdr_len_of(a.container);
     const bool want_crc = a.container == MSL_Z_GZIP, want_adler = a.container == MSL_Z_ZLIB || a.container == MSL_Z_PNG;
@@ -228,16 +238,31 @@ __global__ void __launch_bounds__(kZThreads) deflate_kernel(const ZArgs a) {
     for (unsigned tb = 0; tb < n || tb == 0; tb += kTile) {
         const unsigned tn = min((unsigned)kTile, n - tb);
         // ---- load the tile (image mode inserts the filter byte 0 in front of every scanline)
-        if (!image && (reinterpret_cast<uintptr_t>(src + tb) & 15) == 0) {
-            const uint4* s4 = reinterpret_cast<const uint4*>(src + tb);
-            for (unsigned q = tid; q < (tn >> 4); q += kZThreads) {
-                const uint4 v = __ldg(s4 + q);
-                uint32_t* x32 = reinterpret_cast<uint32_t*>(X + xphys((int)(16 * q)));      // 4-byte aligned (16-byte groups stay inside a segment)
-                x32[0] = v.x; x32[1] = v.y; x32[2] = v.z; x32[3] = v.w;
+        if (!image) {
+            const unsigned long long g0 = r0 + tb;            // raw offset of the tile inside the source
+            if (!a.expand && g0 >= plen && (reinterpret_cast<uintptr_t>(src + (g0 - plen)) & 15) == 0) {
+                const uint8_t* body = src + (g0 - plen);
+                const uint4* s4 = reinterpret_cast<const uint4*>(body);
+                for (unsigned q = tid; q < (tn >> 4); q += kZThreads) {
+                    const uint4 v = __ldg(s4 + q);
+                    uint32_t* x32 = reinterpret_cast<uint32_t*>(X + xphys((int)(16 * q)));      // 4-byte aligned (16-byte groups stay inside a segment)
+                    x32[0] = v.x; x32[1] = v.y; x32[2] = v.z; x32[3] = v.w;
+                }
+                for (unsigned i = (tn & ~15u) + tid; i < tn; i += kZThreads) XP((int)i) = __ldg(body + i);
+            } else {
+                for (unsigned i = tid; i < tn; i += kZThreads) {
+                    const unsigned long long g = g0 + i;
+                    uint8_t v;
+                    if (g < plen) v = __ldg(pfx + g);
+                    else if (!a.expand) v = __ldg(src + (g - plen));
+                    else {
+                        const unsigned long long b = g - plen;
+                        const uint8_t m = __ldg(src + (b >> 2));
+                        v = m ? (uint8_t)(0x3f800000u >> (8 * (unsigned)(b & 3))) : (uint8_t)0;
+                    }
+                    XP((int)i) = v;
+                }
             }
-            for (unsigned i = (tn & ~15u) + tid; i < tn; i += kZThreads) XP((int)i) = __ldg(src + tb + i);
-        } else if (!image) {
-            for (unsigned i = tid; i < tn; i += kZThreads) XP((int)i) = __ldg(src + tb + i);
         } else {
             for (unsigned i = tid; i < tn; i += kZThreads) {
                 const unsigned g = tb + i, r = __umulhi(g, rl_magic), c = g - r * rl;
@@ -483,7 +508,8 @@ size_t deflate_workspace_bytes(int n, int container, size_t raw) {
 }
 
 int launch_deflate_pack(const uint8_t* src, int n, size_t src_pitch, size_t chunk, size_t total, int rows, int row_bytes,
-                        int img_w, int img_ch, int container, int dist2, uint8_t* out, size_t out_cap, unsigned long long* out_off,
+                        int img_w, int img_ch, int container, int dist2, const uint8_t* prefix, size_t prefix_pitch, size_t prefix_len,
+                        int expand, uint8_t* out, size_t out_cap, unsigned long long* out_off,
                         uint32_t* out_meta, void* ws, size_t ws_bytes, cudaStream_t stream) {
     const size_t raw = raw_len_of(chunk, rows, row_bytes);
     if (raw >= (1u << 24)) { set_error("deflate: streams of up to 16 MB (got %zu bytes)", raw); return MSL_ERR_UNSUPPORTED; }
@@ -498,6 +524,8 @@ int launch_deflate_pack(const uint8_t* src, int n, size_t src_pitch, size_t chun
     ZArgs a;
     memset(&a, 0, sizeof(a));
     a.src = src; a.src_pitch = src_pitch; a.total = total; a.chunk = (unsigned)chunk; a.rows = rows; a.row_bytes = row_bytes;
+    a.spv = rows > 0 ? 1u : (unsigned)(total == 0 ? 1 : (total + chunk - 1) / chunk);
+    a.prefix = prefix; a.prefix_pitch = prefix_pitch; a.prefix_len = (unsigned)prefix_len; a.expand = expand;
     a.img_w = img_w; a.img_ch = img_ch; a.container = container; a.dist2 = dist2;
     a.meta = reinterpret_cast<uint32_t*>(ws);
     a.slots = reinterpret_cast<uint8_t*>(ws) + (((size_t)n * 16 + 255) & ~(size_t)255);

@@ -125,7 +125,8 @@ int launch_png_pack(const uint8_t* pixels, int n, int H, int W, int ch, uint8_t*
 size_t deflate_slot_bytes(int container, size_t raw);
 size_t deflate_workspace_bytes(int n, int container, size_t raw);
 int launch_deflate_pack(const uint8_t* src, int n, size_t src_pitch, size_t chunk, size_t total, int rows, int row_bytes,
-                        int img_w, int img_ch, int container, int dist2, uint8_t* out, size_t out_cap, unsigned long long* out_off,
+                        int img_w, int img_ch, int container, int dist2, const uint8_t* prefix, size_t prefix_pitch, size_t prefix_len,
+                        int expand, uint8_t* out, size_t out_cap, unsigned long long* out_off,
                         uint32_t* out_meta, void* ws, size_t ws_bytes, cudaStream_t stream);
 // msl_inflate.cu: inflate (one warp per stream), PNG unfilter, NIfTI payload conversion
 int launch_inflate(const uint8_t* src, size_t src_bytes, const unsigned long long* src_off, int n, int container, uint8_t* dst,

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "msl_deflate_bound": (_sz, [_i, _i, _sz]),
     "msl_deflate_workspace_bytes": (_sz, [_i, _i, _sz]),
     "msl_deflate_chunks": (C.c_int, [_vp, _sz, _sz, _i, _i, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
+    "msl_deflate_files": (C.c_int, [_vp, _i, _sz, _sz, _vp, _sz, _sz, _i, _sz, _i, _i, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
     "msl_png_encode": (C.c_int, [_vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp, _sz, _vp]),
     "msl_inflate": (C.c_int, [_vp, _sz, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "msl_png_unfilter": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -38,11 +38,47 @@ class CodecError(ValueError):
 
 
 # ------------------------------------------------------------------------------------------------ containers (host)
+def gzip_index_member(member_sizes, raw_sizes) -> bytes:
+    """A gzip member with an EMPTY payload whose FEXTRA field ('M','I') lists the compressed and raw size of every
+    preceding member followed by their count: appended to a file written by this package it lets a reader find all
+    member boundaries with one look at the file's tail.  Any gzip reader decodes it to zero bytes."""
+    n = len(member_sizes)
+    body = np.stack([np.asarray(member_sizes, "<u4"), np.asarray(raw_sizes, "<u4")], axis=1).tobytes() + struct.pack("<I", n)
+    if len(body) + 4 > 65535:
+        return b""                                             # too many members for one extra field: readers fall back to hopping
+    return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff" + struct.pack("<H", len(body) + 4) + b"MI" + struct.pack("<H", len(body)) + body
+            + b"\x03\x00" + b"\x00" * 8)
+
+
+def gzip_member_table(data) -> Optional[np.ndarray]:
+    """int64 [n, 3] = (offset, member bytes, raw bytes) of the payload members of a file written by this package, from the
+    index member at its tail (vectorised: no per-member work); None when the file has no such index."""
+    buf = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else data
+    L_ = buf.size
+    if L_ < 40:
+        return None
+    n = int(buf[L_ - 14:L_ - 10].view("<u4")[0])               # ... sizes[n][2], n | 03 00 | crc, isize
+    start = L_ - (10 + 2 + 4 + 8 * n + 4 + 2 + 8)
+    if n <= 0 or start < 0 or bytes(buf[start:start + 4]) != b"\x1f\x8b\x08\x04" or bytes(buf[start + 12:start + 14]) != b"MI":
+        return None
+    t = buf[start + 16:start + 16 + 8 * n].view("<u4").reshape(n, 2).astype(np.int64)
+    off = np.zeros(n, np.int64)
+    np.cumsum(t[:-1, 0], out=off[1:])
+    if off[-1] + t[-1, 0] != start:
+        return None
+    return np.concatenate([off[:, None], t], axis=1)
+
+
 def gzip_members(data: bytes) -> Optional[List[Tuple[int, int, int]]]:
     """[(offset, member bytes, raw bytes)] when `data` is a sequence of gzip members that all carry the 'MS' index
     subfield (files written by this package); None for any other gzip file."""
+    tab = gzip_member_table(data)
+    if tab is not None:
+        return [tuple(int(v) for v in row) for row in tab]
     out, p, n = [], 0, len(data)
     while p < n:
+        if n - p >= 14 and data[p + 12:p + 14] == b"MI" and out:      # the index member at the tail
+            break
         if n - p < 24 or data[p:p + 4] != b"\x1f\x8b\x08\x04" or data[p + 10:p + 16] != b"\x0c\x00MS\x08\x00":
             return None
         msize, raw = struct.unpack_from("<II", data, p + 16)
@@ -116,6 +152,64 @@ def inflate(pieces: Sequence[bytes], raw_sizes: Sequence[int], container: str, d
         if st[i, 1] != raw_sizes[i]:
             raise CodecError(f"stream {i}: decoded {st[i, 1]} bytes, expected {raw_sizes[i]}")
     return dst, dst_off
+
+
+# ---- asynchronous, batch-level forms (device tensors in, device tensors out, nothing synchronises): the building blocks
+# of a pipelined cohort step; the status tensors are checked by the caller when the step's results are collected
+def inflate_device(src: torch.Tensor, src_off: torch.Tensor, dst: torch.Tensor, dst_off: torch.Tensor, container: str,
+                   status: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """msl_inflate on device tensors: stream i = src[src_off[i]:src_off[i+1]] -> dst[dst_off[i]:dst_off[i+1]] (int64 offset
+    tensors of n + 1 entries on the device).  Returns the status tensor int32 [n, 4] (see include/mslesseg.h)."""
+    n = int(src_off.numel()) - 1
+    if status is None:
+        status = torch.empty((n, 4), dtype=torch.int32, device=src.device)
+    cid = {"raw": L.Z_RAW, "zlib": L.Z_ZLIB, "gzip": L.Z_GZIP}[container]
+    L.check(L.load().msl_inflate(ops._ptr(src), src.numel(), ops._ptr(src_off), n, cid, ops._ptr(dst), ops._ptr(dst_off),
+                                 ops._ptr(status), ops._stream()))
+    return status
+
+
+def png_unfilter_device(raw: torch.Tensor, raw_off: torch.Tensor, H: int, W: int, bpp: int, out: torch.Tensor,
+                        status: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """msl_png_unfilter on device tensors: n = out.shape[0] inflated images -> out uint8 [n, H, W] (first channel)."""
+    n = int(out.shape[0])
+    if status is None:
+        status = torch.empty(n, dtype=torch.int32, device=raw.device)
+    L.check(L.load().msl_png_unfilter(ops._ptr(raw), ops._ptr(raw_off), n, H, W, bpp, ops._ptr(out), ops._ptr(status), ops._stream()))
+    return status
+
+
+def nifti_convert_device(payload: torch.Tensor, datatype: int, out: torch.Tensor, inexact: torch.Tensor, slope: float = 1.0,
+                         inter: float = 0.0, scaled: bool = False) -> None:
+    """msl_nifti_convert: out.numel() voxels of NIfTI datatype `datatype` at payload -> out (float32 / uint8 / float64)."""
+    L.check(L.load().msl_nifti_convert(ops._ptr(payload), int(datatype), out.numel(), float(slope), float(inter), 1 if scaled else 0,
+                                       ops._ptr(out) if out.dtype == torch.float32 else None,
+                                       ops._ptr(out) if out.dtype == torch.uint8 else None,
+                                       ops._ptr(out) if out.dtype == torch.float64 else None, ops._ptr(inexact), ops._stream()))
+
+
+def png_table(buf: np.ndarray, file_off: np.ndarray):
+    """Vectorised look at n PNG files stored back to back in `buf` (file i = buf[file_off[i]:file_off[i+1]]) that share
+    the simplest layout - signature, IHDR, ONE IDAT, IEND (what cv2.imwrite and ops.png_encode produce for small images).
+    Returns (width, height, bytes per pixel, idat_start int64 [n], idat_len int64 [n]) or None when a file deviates (the
+    caller then parses file by file with png_parse)."""
+    starts = np.asarray(file_off[:-1], np.int64)
+    sizes = np.diff(np.asarray(file_off, np.int64))
+    if starts.size == 0 or (sizes < 57).any():
+        return None
+    head = buf[starts[:, None] + np.arange(41)[None, :]]                      # [n, 41]
+    sig = np.frombuffer(b"\x89PNG\r\n\x1a\n\x00\x00\x00\rIHDR", np.uint8)
+    if not (head[:, :16] == sig).all() or not (head[:, 37:41] == np.frombuffer(b"IDAT", np.uint8)).all():
+        return None
+    be = lambda a: (a[:, 0].astype(np.int64) << 24) | (a[:, 1].astype(np.int64) << 16) | (a[:, 2].astype(np.int64) << 8) | a[:, 3]
+    w, h, ilen = be(head[:, 16:20]), be(head[:, 20:24]), be(head[:, 33:37])
+    if not ((w == w[0]).all() and (h == h[0]).all() and (head[:, 24:29] == head[0, 24:29]).all() and (ilen + 57 == sizes).all()):
+        return None
+    depth, ctype, comp, filt, interlace = (int(v) for v in head[0, 24:29])
+    bpp = {0: 1, 2: 3, 4: 2, 6: 4}.get(ctype)
+    if depth != 8 or bpp is None or interlace or comp or filt:
+        raise CodecError(f"PNG variant not supported by the device decoder (bit depth {depth}, colour type {ctype}, interlace {interlace})")
+    return int(w[0]), int(h[0]), bpp, starts + 41, ilen
 
 
 def png_decode_first_channel(files: Sequence[bytes], device) -> torch.Tensor:
@@ -249,24 +343,41 @@ def nifti_header_bytes(shape_xyz, np_dtype, affine) -> bytes:
     return bytes(hdr)
 
 
-def nifti_gz_device(vol_zyx: torch.Tensor, affine, dist2: Optional[int] = None) -> ops.PackedStreams:
-    """The bytes of a .nii.gz file for a device volume [Z][Y][X] (float32, uint8, float64, int16, int32, int8): header + voxels deflated on the GPU in
-    64 KB members (reference utils/utils.py:173-181 guardar_volumen).  `b"".join(ps.files())` / ps.to_host() is the file."""
-    ops._need_cuda(vol_zyx, "vol_zyx")
-    Z, Y, X = (int(d) for d in vol_zyx.shape)
+def nifti_gz_device(vol: torch.Tensor, affine, dist2: Optional[int] = None, como_float32: bool = False,
+                    out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> ops.PackedStreams:
+    """The gzip members of the .nii.gz file(s) of device volumes [Z][Y][X] or [n][Z][Y][X] (float32, uint8, float64, int16,
+    int32, int8): header (a 352-byte prefix, never concatenated with the voxels) + voxels deflated on the GPU in 64 KB
+    members (reference utils/utils.py:173-181 guardar_volumen).  como_float32: the volume is a uint8 {0, 1} mask but the
+    file stores float32 (what reconstruir_volumen writes).  ps.streams_per_file members belong to each volume."""
+    ops._need_cuda(vol, "vol")
+    v4 = vol if vol.dim() == 4 else vol[None]
+    n, Z, Y, X = (int(d) for d in v4.shape)
     npdt = {torch.float32: np.float32, torch.uint8: np.uint8, torch.float64: np.float64, torch.int16: np.int16,
-            torch.int32: np.int32, torch.int8: np.int8}[vol_zyx.dtype]
-    hdr = torch.from_numpy(np.frombuffer(nifti_header_bytes((X, Y, Z), npdt, affine), np.uint8).copy()).to(vol_zyx.device)
-    buf = torch.cat([hdr, vol_zyx.contiguous().reshape(-1).view(torch.uint8)])
+            torch.int32: np.int32, torch.int8: np.int8}[v4.dtype]
+    if como_float32:
+        if v4.dtype != torch.uint8:
+            raise ValueError("como_float32 expects a uint8 mask volume")
+        npdt = np.float32
+    hdr = torch.from_numpy(np.frombuffer(nifti_header_bytes((X, Y, Z), npdt, affine), np.uint8).copy()).to(v4.device, non_blocking=True)
     if dist2 is None:
-        dist2 = vol_zyx.element_size() if vol_zyx.element_size() > 1 else 0
-    return ops.deflate_chunks(buf, chunk_len=CHUNK, container="gzip", dist2=dist2)
+        dist2 = np.dtype(npdt).itemsize if np.dtype(npdt).itemsize > 1 else 0
+    return ops.deflate_files(v4.contiguous(), prefix=hdr, expand_u8_to_f32=como_float32, chunk_len=CHUNK, container="gzip",
+                             dist2=dist2, out=out, workspace=workspace)
+
+
+def nifti_gz_bytes(ps: ops.PackedStreams, archivo: int = 0) -> bytes:
+    """The complete .nii.gz of file `archivo` of nifti_gz_device: its members + the index member (gzip_index_member)."""
+    data, off = ps.to_host()
+    meta = ps.meta.cpu().numpy().astype(np.int64) & 0xffffffff
+    spv = getattr(ps, "streams_per_file", len(off) - 1)
+    a, b = archivo * spv, (archivo + 1) * spv
+    return data[int(off[a]):int(off[b])].tobytes() + gzip_index_member(np.diff(off[a:b + 1]), meta[a:b, 1])
 
 
 def nifti_save_device(vol_zyx: torch.Tensor, affine, path) -> int:
     """Writes the .nii.gz; returns the file size."""
-    data, off = nifti_gz_device(vol_zyx, affine).to_host()
+    blob = nifti_gz_bytes(nifti_gz_device(vol_zyx, affine))
     Path(path).parent.mkdir(parents=True, exist_ok=True)
     with open(path, "wb") as f:
-        f.write(data[:int(off[-1])].tobytes())
-    return int(off[-1])
+        f.write(blob)
+    return len(blob)

@@ -90,6 +90,13 @@ def reconstruir_volumen(pred_masks_dir, volumen_referencia, output_path, plano):
     for (archivo, i), (w, h) in zip(indices, geos):
         validar_corte(int(i), np.empty((h, w), dtype=np.uint8), shape_original, plano)   # index range + exact slice shape (:153-176)
     st = _codec.png_decode_first_channel(archivos, device())                 # [n, rows, cols] uint8, slice orientation
-    vol = ops.recon(st, [0] * len(indices), [int(i) for _, i in indices], plano, 1, (X, Y, Z), dtype=torch.float32)
-    guardar_volumen(vol[0], affine, output_path)
-    return np.asfortranarray(vol[0].cpu().numpy().transpose(2, 1, 0))
+    vol = ops.recon(st, [0] * len(indices), [int(i) for _, i in indices], plano, 1, (X, Y, Z))        # uint8 {0, 1} on the device
+    try:
+        blob = _codec.nifti_gz_bytes(_codec.nifti_gz_device(vol[0], affine, como_float32=True))     # the file stores float32 (:202)
+        Path(output_path).parent.mkdir(parents=True, exist_ok=True)
+        with open(output_path, "wb") as f:
+            f.write(blob)
+    except Exception as e:
+        logger.error(f"❌ Error al guardar el volumen en {output_path}: {e}")
+        raise
+    return np.asfortranarray(vol[0].cpu().numpy().transpose(2, 1, 0).astype(np.float32))

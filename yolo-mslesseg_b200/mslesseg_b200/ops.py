@@ -408,6 +408,45 @@ def deflate_chunks(src: torch.Tensor, chunk_len: int = 65536, container: str = "
     return PackedStreams(out, off, meta)
 
 
+def deflate_files(bodies: torch.Tensor, prefix: Optional[torch.Tensor] = None, expand_u8_to_f32: bool = False, chunk_len: int = 65536,
+                  container: str = "gzip", dist2: int = 0, out: Optional[torch.Tensor] = None,
+                  workspace: Optional[torch.Tensor] = None) -> PackedStreams:
+    """nfiles = bodies.shape[0] files in one launch: file f = prefix (one for all, or [nfiles, prefix_len]) + bodies[f]
+    (any dtype, contiguous), cut into chunks of chunk_len bytes, every chunk its own deflate stream; streams are numbered
+    file-major, `streams_per_file` of them per file.  expand_u8_to_f32: bodies are uint8 masks stored as float32 0 / 1."""
+    _need_cuda(bodies, "bodies")
+    lib = L.load()
+    cid = _CONTAINER_ID[container]
+    nfiles = int(bodies.shape[0])
+    body_len = (bodies.numel() // max(nfiles, 1)) * bodies.element_size()
+    plen, ppitch = 0, 0
+    if prefix is not None:
+        _need_cuda(prefix, "prefix")
+        if prefix.dtype != torch.uint8 or prefix.dim() not in (1, 2) or (prefix.dim() == 2 and prefix.shape[0] != nfiles):
+            raise ValueError("prefix must be uint8 [prefix_len] or [nfiles, prefix_len]")
+        plen = int(prefix.shape[-1])
+        ppitch = plen if prefix.dim() == 2 else 0
+    if expand_u8_to_f32 and bodies.dtype != torch.uint8:
+        raise ValueError("expand_u8_to_f32 needs uint8 bodies")
+    total = plen + body_len * (4 if expand_u8_to_f32 else 1)
+    spv = max(1, -(-total // chunk_len))
+    n = spv * nfiles
+    cap = int(lib.msl_deflate_bound(n, cid, chunk_len))
+    if out is None:
+        out = torch.empty(cap, dtype=torch.uint8, device=bodies.device)
+    need = int(lib.msl_deflate_workspace_bytes(n, cid, chunk_len))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=bodies.device)
+    off = torch.empty(n + 1, dtype=torch.int64, device=bodies.device)
+    meta = torch.empty((n, 4), dtype=torch.int32, device=bodies.device)
+    L.check(lib.msl_deflate_files(_ptr(bodies), nfiles, body_len, body_len, _ptr(prefix), ppitch, plen, 1 if expand_u8_to_f32 else 0,
+                                  chunk_len, cid, dist2, _ptr(out), out.numel(), _ptr(off), _ptr(meta), _ptr(workspace),
+                                  workspace.numel(), _stream()))
+    ps = PackedStreams(out, off, meta)
+    ps.streams_per_file = spv
+    return ps
+
+
 def png_encode(pixels: torch.Tensor, out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> PackedStreams:
     """Compressed PNG files for a batch of images: uint8 [n, H, W, C] (C = 4 RGBA - what plt.imsave writes, reference
     scripts/extraer_dataset.py:192,197 - or 2 / 3) or [n, H, W] (gray, what cv2.imwrite writes for masks).  The files are
