@@ -213,8 +213,8 @@ int msl_png_encode(const uint8_t* pixels, int n, int H, int W, int channels,
  *
  * msl_nifti_convert: nvox voxels of NIfTI datatype code `datatype` (2 uint8, 4 int16, 8 int32, 16 float32, 64 float64,
  * 256 int8, 512 uint16, 768 uint32; little endian, any alignment), scaled by slope / inter when scaled != 0 (get_fdata
- * semantics, float64 arithmetic), to out_f32 / out_u8 / out_f64 (any may be NULL).  *inexact (DEVICE uint64) counts the
- * values the float32 / uint8 output could not hold exactly (float64 holds every value get_fdata() yields). */
+ * semantics, float64 arithmetic), to out_f32 / out_u8 / out_f64 (any may be NULL).  *inexact (DEVICE uint64, zeroed by the caller) is
+ * incremented by the number of values the float32 / uint8 output could not hold exactly (float64 holds every value get_fdata() yields). */
 int msl_inflate(const uint8_t* src, size_t src_bytes, const uint64_t* src_off, int n, int container,
                 uint8_t* dst, const uint64_t* dst_off, uint32_t* status, msl_stream_t stream);
 int msl_png_unfilter(uint8_t* raw, const uint64_t* raw_off, int n, int H, int W, int bytes_per_pixel,

@@ -68,3 +68,20 @@ def test_single_process_is_identity():
     assert np.array_equal(table.numpy(), np.stack([_fake_counts(p) for p in ["P1", "P2", "P3"]]))
     assert D.shard_patients(ids, 1, 0) == ["P1", "P2", "P3"]
     assert D.shard_patients([f"P{n}" for n in range(1, 54)], 2, 1, k_folds=5) == [f"P{n}" for n in range(12, 23)] + [f"P{n}" for n in range(34, 44)]
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_cohort75_sharding_partitions_the_cohort(world):
+    """bench.py --config cohort75 / stress: every patient on exactly one rank; fold-major while there are at least as many
+    folds as ranks (5 folds: 1, 2, 4 ranks), round-robin on the sorted list beyond that (8 ranks)."""
+    ids = [f"P{n}" for n in range(1, 76)]
+    shards = [D.shard_patients(ids, world, r, k_folds=5, n_ids=75) for r in range(world)]
+    assert sorted(sum(shards, []), key=D.patient_number) == D.sort_patients(ids)
+    if world <= 5:
+        for r, sh in enumerate(shards):
+            assert {(M.calcular_fold(p, 5, 75) - 1) % world for p in sh} <= {r}
+    else:
+        assert shards[3] == D.sort_patients(ids)[3::world]
+    assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 15
+    # the generalised fold rule keeps the reference's assignment for the real cohort (P1..P53, 5 folds)
+    assert [M.calcular_fold(f"P{n}", 5) for n in (1, 11, 12, 22, 23, 33, 34, 43, 44, 53)] == [1, 1, 2, 2, 3, 3, 4, 4, 5, 5]

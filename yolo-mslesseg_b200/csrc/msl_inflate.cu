@@ -428,7 +428,6 @@ int launch_png_unfilter(uint8_t* raw, const unsigned long long* raw_off, int n, 
 int launch_nifti_convert(const uint8_t* payload, int datatype, unsigned long long nvox, double slope, double inter, int scaled,
                          float* out_f32, uint8_t* out_u8, double* out_f64, unsigned long long* inexact, cudaStream_t stream) {
     if (nvox == 0) return MSL_OK;
-    MSL_CUDA_CHECK(cudaMemsetAsync(inexact, 0, sizeof(unsigned long long), stream));
     ProfScope prof(K_NIFTI_CONVERT, stream);
     const int blocks = (int)((nvox + 256ull * 8 - 1) / (256ull * 8) < 148 * 16 ? (nvox + 256ull * 8 - 1) / (256ull * 8) : 148 * 16);
     nifti_convert_kernel<<<blocks, 256, 0, stream>>>(payload, datatype, nvox, slope, inter, scaled, out_f32, out_u8, out_f64, inexact);

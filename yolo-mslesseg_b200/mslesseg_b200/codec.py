@@ -127,6 +127,7 @@ def _pack_streams(pieces: Sequence[bytes], device) -> Tuple[torch.Tensor, np.nda
     return host.to(device, non_blocking=True), off
 
 
+@ops._nvtx("inflate")
 def inflate(pieces: Sequence[bytes], raw_sizes: Sequence[int], container: str, device) -> Tuple[torch.Tensor, np.ndarray]:
     """Inflates n streams on the device (one warp each).  raw_sizes: the exact decoded size of every stream (known from
     the container: gzip ISIZE / 'MS' subfield, PNG geometry).  Returns (device bytes, offsets [n + 1]); stream i decodes
@@ -156,6 +157,7 @@ def inflate(pieces: Sequence[bytes], raw_sizes: Sequence[int], container: str, d
 
 # ---- asynchronous, batch-level forms (device tensors in, device tensors out, nothing synchronises): the building blocks
 # of a pipelined cohort step; the status tensors are checked by the caller when the step's results are collected
+@ops._nvtx("inflate_device")
 def inflate_device(src: torch.Tensor, src_off: torch.Tensor, dst: torch.Tensor, dst_off: torch.Tensor, container: str,
                    status: Optional[torch.Tensor] = None) -> torch.Tensor:
     """msl_inflate on device tensors: stream i = src[src_off[i]:src_off[i+1]] -> dst[dst_off[i]:dst_off[i+1]] (int64 offset
@@ -169,6 +171,7 @@ def inflate_device(src: torch.Tensor, src_off: torch.Tensor, dst: torch.Tensor, 
     return status
 
 
+@ops._nvtx("png_unfilter_device")
 def png_unfilter_device(raw: torch.Tensor, raw_off: torch.Tensor, H: int, W: int, bpp: int, out: torch.Tensor,
                         status: Optional[torch.Tensor] = None) -> torch.Tensor:
     """msl_png_unfilter on device tensors: n = out.shape[0] inflated images -> out uint8 [n, H, W] (first channel)."""
@@ -179,6 +182,7 @@ def png_unfilter_device(raw: torch.Tensor, raw_off: torch.Tensor, H: int, W: int
     return status
 
 
+@ops._nvtx("nifti_convert_device")
 def nifti_convert_device(payload: torch.Tensor, datatype: int, out: torch.Tensor, inexact: torch.Tensor, slope: float = 1.0,
                          inter: float = 0.0, scaled: bool = False) -> None:
     """msl_nifti_convert: out.numel() voxels of NIfTI datatype `datatype` at payload -> out (float32 / uint8 / float64)."""
@@ -212,6 +216,7 @@ def png_table(buf: np.ndarray, file_off: np.ndarray):
     return int(w[0]), int(h[0]), bpp, starts + 41, ilen
 
 
+@ops._nvtx("png_decode_first_channel")
 def png_decode_first_channel(files: Sequence[bytes], device) -> torch.Tensor:
     """uint8 [n, H, W] on the device: channel 0 of n PNG files of one geometry (what cargar_y_preprocesar_imagen keeps,
     reference scripts/reconstruir_volumen.py:141-145).  Inflate and scanline unfiltering run on the GPU."""
@@ -277,6 +282,7 @@ def nifti_read_header(path):
     return shape, affine
 
 
+@ops._nvtx("nifti_load_device")
 def nifti_load_device(path, device, dtype=torch.float32):
     """(volume [Z][Y][X] on the device as float32, uint8 or float64, shape (X, Y, Z), affine).  The file bytes are uploaded
     as they are; inflate + datatype conversion (+ scl_slope / scl_inter) run on the GPU.  uint8 output demands integral
@@ -343,6 +349,7 @@ def nifti_header_bytes(shape_xyz, np_dtype, affine) -> bytes:
     return bytes(hdr)
 
 
+@ops._nvtx("nifti_gz_device")
 def nifti_gz_device(vol: torch.Tensor, affine, dist2: Optional[int] = None, como_float32: bool = False,
                     out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> ops.PackedStreams:
     """The gzip members of the .nii.gz file(s) of device volumes [Z][Y][X] or [n][Z][Y][X] (float32, uint8, float64, int16,

@@ -25,6 +25,23 @@ _LAYOUT_ID = {"G": L.OUT_G, "P": L.OUT_P, "PNG_GRAY": L.OUT_PNG_GRAY, "PNG_RGBA"
 _tables_cache: Dict[tuple, torch.Tensor] = {}
 
 
+def _nvtx(name: str):
+    """Decorator: an NVTX range per stage call, so that an nsys / ncu timeline of a cohort step reads as
+    stages.  torch.cuda.nvtx is a no-op without a profiler attached."""
+    def deco(fn):
+        import functools
+
+        @functools.wraps(fn)
+        def wrapper(*a, **k):
+            torch.cuda.nvtx.range_push("msl." + name)
+            try:
+                return fn(*a, **k)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return wrapper
+    return deco
+
+
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -88,6 +105,7 @@ def _out_shape(n: int, rows: int, cols: int, layout: str):
 
 
 # ------------------------------------------------------------------------------------ E0
+@_nvtx("lesion_slices")
 def lesion_slices(gt: torch.Tensor):
     """any(mask_slice > 0) for every slice of the three planes.  gt: [nvol, Z, Y, X] uint8/float32.
     Returns (any_ax [nvol, Z], any_co [nvol, Y], any_sa [nvol, X]) uint8."""
@@ -103,6 +121,7 @@ def lesion_slices(gt: torch.Tensor):
 
 
 # ------------------------------------------------------------------------------------ E1-E8
+@_nvtx("slice_ranges")
 def slice_ranges(vol: torch.Tensor) -> Dict[str, torch.Tensor]:
     """{plano: float32 [nvol, n_plane, 2]} = (min, max) of every slice of the three planes in one pass over the float32
     volumes [nvol, Z, Y, X] (the statistics of normalizar_a_uint8, reference utils/utils.py:400-405)."""
@@ -115,6 +134,7 @@ def slice_ranges(vol: torch.Tensor) -> Dict[str, torch.Tensor]:
     return {"axial": out[:, :Z], "coronal": out[:, Z:Z + Y], "sagital": out[:, Z + Y:]}
 
 
+@_nvtx("enhance_slices")
 def enhance_slices(vol: torch.Tensor, mejora: Optional[str], plano: str, vol_of_slice=None, idx_of_slice=None,
                    layout: str = "G", out: Optional[torch.Tensor] = None, lut_out: str = "gray") -> torch.Tensor:
     """Enhanced slices of resident volumes.  vol: [nvol, Z, Y, X] float32 (normalised per slice like
@@ -132,13 +152,26 @@ def enhance_slices(vol: torch.Tensor, mejora: Optional[str], plano: str, vol_of_
     if vol_of_slice is None:
         ns, vs, ix = nvol * n_p, None, None
     else:
+        checked = False
+        if not isinstance(vol_of_slice, torch.Tensor) and not isinstance(idx_of_slice, torch.Tensor):
+            # host lists are range-checked here; the reference raises IndexError for such a slice index (the kernel skips
+            # (volume, index) pairs outside the volumes)
+            hv, hi = np.asarray(vol_of_slice, dtype=np.int64).reshape(-1), np.asarray(idx_of_slice, dtype=np.int64).reshape(-1)
+            if hv.size and (hv.min() < 0 or hv.max() >= nvol):
+                raise IndexError(f"volume index outside [0, {nvol})")
+            if hi.size and (hi.min() < 0 or hi.max() >= n_p):
+                raise IndexError(f"index {int(hi.max() if hi.max() >= n_p else hi.min())} is out of bounds for plano {plano} with size {n_p}")
+            checked = True
         vs, ix = _index_tensor(vol_of_slice, vol.device), _index_tensor(idx_of_slice, vol.device)
         if vs.shape != ix.shape or vs.dim() != 1:
             raise ValueError("vol_of_slice / idx_of_slice must be 1-D and of equal length")
         ns = int(vs.numel())
     shape = _out_shape(ns, rows, cols, layout)
     if out is None:
-        out = torch.empty(shape, dtype=torch.uint8, device=vol.device)
+        # index lists that live on the device cannot be checked without a synchronisation: slices whose pair lies outside
+        # the volumes are skipped by the kernel and come back as zeros instead of uninitialised memory
+        unchecked = vol_of_slice is not None and not checked
+        out = (torch.zeros if unchecked else torch.empty)(shape, dtype=torch.uint8, device=vol.device)
     else:
         _need_cuda(out, "out")
         if tuple(out.shape) != shape or out.dtype != torch.uint8:
@@ -152,6 +185,7 @@ def enhance_slices(vol: torch.Tensor, mejora: Optional[str], plano: str, vol_of_
     return out
 
 
+@_nvtx("enhance_images")
 def enhance_images(imgs: torch.Tensor, mejora: Optional[str], layout: str = "G", lut_out: str = "gray") -> torch.Tensor:
     """Batch of C-contiguous 2-D images [n, rows, cols] (float32 or uint8) -> enhanced gray images."""
     _need_cuda(imgs, "imgs")
@@ -172,6 +206,7 @@ def enhance_volumes_workspace_bytes(nvol: int, X: int, Y: int, Z: int) -> int:
     return int(L.load().msl_workspace_bytes(L.WS_ENHANCE_VOLUMES, nvol, X, Y, Z))
 
 
+@_nvtx("enhance_volumes")
 def enhance_volumes(vol: torch.Tensor, mejoras: Iterable[str] = MEJORAS, planos: Iterable[str] = PLANOS,
                     outs: Optional[Dict[Tuple[str, str], torch.Tensor]] = None,
                     workspace: Optional[torch.Tensor] = None,
@@ -217,6 +252,7 @@ def enhance_volumes(vol: torch.Tensor, mejoras: Iterable[str] = MEJORAS, planos:
 
 
 # ------------------------------------------------------------------------------------ R0
+@_nvtx("combine_predictions")
 def combine_predictions(masks: Optional[torch.Tensor], inst_offset, rows: int, cols: int, layout: str = "G",
                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """YOLO instance masks -> one predicted mask per slice (reference scripts/generar_predicciones.py:123-140).
@@ -233,14 +269,19 @@ def combine_predictions(masks: Optional[torch.Tensor], inst_offset, rows: int, c
         if masks.dtype != torch.float32 or masks.dim() != 3:
             raise ValueError("masks must be float32 [n_inst, mh, mw]")
         dev, masks_ptr, mh, mw = masks.device, _ptr(masks), int(masks.shape[1]), int(masks.shape[2])
+    n_inst = 0 if masks is None else int(masks.shape[0])
+    if not isinstance(inst_offset, torch.Tensor):
+        # a host table is validated on the host (no synchronisation); a table that already lives on the device is
+        # trusted - checking it would cost a blocking device-to-host copy on every call
+        host_off = [int(v) for v in np.asarray(inst_offset).reshape(-1)]
+        if not host_off:
+            raise ValueError("inst_offset needs n + 1 entries")
+        if host_off[0] != 0 or host_off[-1] != n_inst or any(b < a for a, b in zip(host_off, host_off[1:])):
+            raise ValueError("inst_offset must be a non-decreasing prefix table from 0 to the number of instance masks")
     off = _index_tensor(inst_offset, dev)
     n = int(off.numel()) - 1
     if n < 0:
         raise ValueError("inst_offset needs n + 1 entries")
-    n_inst = 0 if masks is None else int(masks.shape[0])
-    host_off = off.cpu().tolist()
-    if host_off[0] != 0 or host_off[-1] != n_inst or any(b < a for a, b in zip(host_off, host_off[1:])):
-        raise ValueError("inst_offset must be a non-decreasing prefix table from 0 to the number of instance masks")
     shape = (n, rows, cols) if layout == "G" else (n, cols, rows)
     if out is None:
         out = torch.empty(shape, dtype=torch.uint8, device=dev)
@@ -253,6 +294,7 @@ def combine_predictions(masks: Optional[torch.Tensor], inst_offset, rows: int, c
 
 
 # ------------------------------------------------------------------------------------ R1-R2
+@_nvtx("recon")
 def recon(slices: torch.Tensor, vol_of_slice, idx_of_slice, plano: str, nvol: int, shape_xyz: Sequence[int],
           dtype: torch.dtype = torch.uint8, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Predicted masks [n, rows, cols] uint8 (pixel > 0 = lesion) -> volumes [nvol, Z, Y, X] of 0/1."""
@@ -271,6 +313,10 @@ def recon(slices: torch.Tensor, vol_of_slice, idx_of_slice, plano: str, nvol: in
         raise TypeError("dtype must be torch.uint8 or torch.float32")
     if out is None:
         out = torch.empty((nvol, Z, Y, X), dtype=dtype, device=dev)
+    else:
+        _need_cuda(out, "out")
+        if tuple(out.shape) != (nvol, Z, Y, X) or out.dtype not in (torch.uint8, torch.float32) or out.device != dev:
+            raise ValueError(f"out must be a contiguous uint8 / float32 CUDA tensor {(nvol, Z, Y, X)} on {dev}")
     ws_bytes = int(L.load().msl_workspace_bytes(L.WS_RECON, nvol, X, Y, Z))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     u8 = out if out.dtype == torch.uint8 else None
@@ -281,6 +327,7 @@ def recon(slices: torch.Tensor, vol_of_slice, idx_of_slice, plano: str, nvol: in
 
 
 # ------------------------------------------------------------------------------------ R3-R4
+@_nvtx("consensus_eval")
 def consensus_eval(ax: torch.Tensor, co: torch.Tensor, sa: torch.Tensor, gt: Optional[torch.Tensor] = None,
                    umbral: int = 2, want_consenso: bool = True):
     """(ax + co + sa >= umbral) and, when gt is given, int64 counts [nvol, 4 planes, (tp, fp, fn, tn)]
@@ -303,6 +350,7 @@ def consensus_eval(ax: torch.Tensor, co: torch.Tensor, sa: torch.Tensor, gt: Opt
     return cons, counts
 
 
+@_nvtx("confusion_counts")
 def confusion_counts(gt: torch.Tensor, pred: torch.Tensor) -> torch.Tensor:
     """int64 [nvol, (tp, fp, fn, tn)] with the reference's exact ==1 / ==0 predicates."""
     _need_cuda(gt, "gt")
@@ -316,6 +364,7 @@ def confusion_counts(gt: torch.Tensor, pred: torch.Tensor) -> torch.Tensor:
     return counts
 
 
+@_nvtx("slice_counts")
 def slice_counts(gt: torch.Tensor, pred: torch.Tensor) -> Dict[str, torch.Tensor]:
     """Per-slice (tp, fp, fn, tn) of every slice of the three planes in one pass (the counts behind
     extras/visualizar_prediccion_corte.py seleccionar_mejor_corte).  gt, pred: uint8 [nvol, Z, Y, X].
@@ -385,6 +434,7 @@ class PackedStreams:
         return [data[off[i]:off[i + 1]].tobytes() for i in range(len(off) - 1)]
 
 
+@_nvtx("deflate_chunks")
 def deflate_chunks(src: torch.Tensor, chunk_len: int = 65536, container: str = "gzip", dist2: int = 0,
                    out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> PackedStreams:
     """Cuts the bytes of `src` (any contiguous CUDA tensor) into chunks of chunk_len bytes and deflates every chunk into
@@ -408,6 +458,7 @@ def deflate_chunks(src: torch.Tensor, chunk_len: int = 65536, container: str = "
     return PackedStreams(out, off, meta)
 
 
+@_nvtx("deflate_files")
 def deflate_files(bodies: torch.Tensor, prefix: Optional[torch.Tensor] = None, expand_u8_to_f32: bool = False, chunk_len: int = 65536,
                   container: str = "gzip", dist2: int = 0, out: Optional[torch.Tensor] = None,
                   workspace: Optional[torch.Tensor] = None) -> PackedStreams:
@@ -447,6 +498,7 @@ def deflate_files(bodies: torch.Tensor, prefix: Optional[torch.Tensor] = None, e
     return ps
 
 
+@_nvtx("png_encode")
 def png_encode(pixels: torch.Tensor, out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> PackedStreams:
     """Compressed PNG files for a batch of images: uint8 [n, H, W, C] (C = 4 RGBA - what plt.imsave writes, reference
     scripts/extraer_dataset.py:192,197 - or 2 / 3) or [n, H, W] (gray, what cv2.imwrite writes for masks).  The files are
@@ -471,6 +523,7 @@ def png_encode(pixels: torch.Tensor, out: Optional[torch.Tensor] = None, workspa
 
 
 # ------------------------------------------------------------------------------------ label polygons
+@_nvtx("mask_contours")
 def mask_contours(masks: torch.Tensor, value: int = 0, max_contours: int = 256, max_points: int = 8192):
     """External contours of binary masks uint8 [n, H, W], as cv2.findContours(mask == value (or mask != 0 when value is
     0), RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) returns them (reference scripts/extraer_dataset.py:215-227 via ultralytics).
@@ -511,6 +564,7 @@ def mask_contours(masks: torch.Tensor, value: int = 0, max_contours: int = 256, 
 
 
 # ------------------------------------------------------------------------------------ host hand-off
+@_nvtx("nonzero_flags")
 def nonzero_flags(stack: torch.Tensor, out=None):
     """Which slices and rows of a uint8 stack [nvol, A, B, C] hold a non-zero byte: (any_a [nvol, A], any_b [nvol, B]).
     out: optional pair of contiguous uint8 device tensors of those shapes (e.g. views of one buffer that goes to the host
