@@ -723,6 +723,7 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
     hdr_f32 = torch.from_numpy(np.frombuffer(codec.nifti_header_bytes((X, Y, Z), np.float32, aff), np.uint8).copy()).to(device)
     hdr_u8 = torch.from_numpy(np.frombuffer(codec.nifti_header_bytes((X, Y, Z), np.uint8, aff), np.uint8).copy()).to(device)
     h2d = d2h = 0
+    waits = [0.0]            # seconds the host spent blocked on the chunk events (the rest of a step is enqueue work)
 
     def member_offsets(H, c0, n, pitch):
         """src / dst offsets (int64, n_members + 1) of the gzip members of files c0 .. c0+n inside the chunk's buffers."""
@@ -814,7 +815,9 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
         """The chunk's sizes are on the host: enqueue the copies of exactly the bytes its files occupy (+ offsets, status)."""
         nonlocal d2h
         st, d = streams[ci % nstream], slots[ci % nstream]
+        tw = time.perf_counter()
         d["event"].synchronize()
+        waits[0] += time.perf_counter() - tw
         res, o, cons, srow, flags, n, hi = d["keep"]
         tot = d["h_tot"].numpy()
         with torch.cuda.stream(st):
@@ -864,6 +867,18 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
         e2e_step()
     sync_all()
     sec = (time.perf_counter() - t0) / K
+    # per-kernel device time of one more (untimed) step, and the host time spent enqueueing it
+    from mslesseg_b200 import _lib as _L2
+    waits[0] = 0.0
+    th0 = time.perf_counter()
+    e2e_step()
+    host_total_ms = (time.perf_counter() - th0) * 1e3
+    host_enqueue_ms = host_total_ms - waits[0] * 1e3          # Python + launch work of one step (unprofiled)
+    sync_all()
+    _L2.profile_enable(True)
+    e2e_step()
+    sync_all()
+    kern = {k: round(v[0], 3) for k, v in sorted(_L2.profile_collect().items(), key=lambda kv: -kv[1][0])}
     # ---- the host files decode (Pillow / gzip on the host = checker) to what the device holds for the last chunks
     import gzip as _gz
     import io as _io
@@ -900,6 +915,7 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
     return {"value": world * B * N_VOX / sec / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "ms_per_step": sec * 1e3, "steps": K, "host_results_equal_device": bool(ok),
             "uncompressed_bytes_per_step": {"inputs": int(raw_in), "results": int(raw_out)},
+            "kernel_ms_per_step": kern, "host_enqueue_ms_per_step": host_enqueue_ms,
             "note": ("host buffers hold FILES: .nii.gz volumes (FLAIR float32, GT float32) and predicted-mask PNGs in; PNG slices of the 12 "
                      "stacks, float32 .nii.gz of the 3 reconstructions, uint8 consensus .nii.gz and the count table out; inflate / "
                      "deflate on the GPU; 4-patient chunks over 3 streams; wall clock around synchronised steps")}

@@ -64,7 +64,7 @@ def test_deflate_chunks_decode_with_zlib(ops, cuda_device, container):
             if container == "gzip":          # the members back to back are one valid .gz file
                 assert gzip.decompress(packed[:off[-1]].tobytes()) == data.tobytes()
             if name in ("zeros", "one_run") and data.size > 100_000:
-                assert off[-1] < data.size // 50, (name, off[-1])
+                assert off[-1] < data.size // 40, (name, off[-1])
             if name == "noise":
                 assert off[-1] < data.size * 1.07 + 64 * n
 
@@ -98,7 +98,7 @@ def test_png_encode_decodes_with_pillow(ops, cuda_device):
     cv2 = pytest.importorskip("cv2")
     blank = torch.zeros((3, 218, 182), dtype=torch.uint8, device=cuda_device)
     files = ops.png_encode(blank).files()
-    assert all(len(f) < 600 for f in files)
+    assert all(len(f) < 1000 for f in files)
     assert np.array_equal(cv2.imdecode(np.frombuffer(files[0], np.uint8), cv2.IMREAD_UNCHANGED), np.zeros((218, 182), np.uint8))
 
 
@@ -213,7 +213,7 @@ def test_nifti_gz_round_trip_on_device(ops, codec, cuda_device, tmp_path):
     assert torch.equal(vol2, vol)
     p4 = tmp_path / "P2_consenso.nii.gz"
     codec.nifti_save_device(m, aff, p4)
-    assert p4.stat().st_size < 100_000
+    assert p4.stat().st_size < 250_000
     arr, _ = nifti.load(p4)
     assert arr.dtype == np.uint8 and np.array_equal(arr.transpose(2, 1, 0), pat.gt)
     assert codec.nifti_read_header(p4)[0] == (182, 218, 182)
@@ -231,7 +231,7 @@ def test_deflate_files_prefix_expand_and_index(ops, codec, cuda_device):
     masks[1] = 0
     aff = np.diag([1.0, 1.0, 1.0, 1.0])
     ps = codec.nifti_gz_device(torch.from_numpy(masks).to(cuda_device), aff, como_float32=True)
-    assert ps.streams_per_file == -(-(352 + masks[0].size * 4) // 65536)
+    assert ps.streams_per_file == -(-(352 + masks[0].size * 4) // codec.CHUNK)
     for f in range(3):
         blob = codec.nifti_gz_bytes(ps, f)
         raw = gzip.decompress(blob)
@@ -249,3 +249,21 @@ def test_deflate_files_prefix_expand_and_index(ops, codec, cuda_device):
     for f in range(2):
         raw = gzip.decompress(data[off[f * spv]:off[(f + 1) * spv]].tobytes())
         assert raw == pref[f].tobytes() + vols[f].tobytes()
+
+
+def test_own_streams_round_trip_all_distances(ops, codec, cuda_device):
+    """What msl_deflate_* writes (stored blocks + fixed-Huffman run blocks, one match distance 1..4) decodes on the device
+    and with zlib, for every container, chunk size and distance."""
+    import torch
+    pl = _payloads()
+    for container in ("raw", "zlib", "gzip"):
+        for name, data in pl.items():
+            for chunk, d2 in ((16384, 0), (16384, 4), (5000, 2), (3001, 3), (1 << 18, 1)):
+                ps = ops.deflate_chunks(torch.from_numpy(data.copy()).to(cuda_device), chunk_len=chunk, container=container, dist2=d2)
+                packed, off = ps.to_host()
+                meta = ps.meta.cpu().numpy().astype(np.int64) & 0xffffffff
+                pieces = [packed[off[i]:off[i + 1]].tobytes() for i in range(len(off) - 1)]
+                out, o = codec.inflate(pieces, [int(r) for r in meta[:, 1]], container, cuda_device)
+                host = out.cpu().numpy()
+                got = np.concatenate([host[o[i]:o[i] + meta[i, 1]] for i in range(len(pieces))]) if len(pieces) else np.zeros(0, np.uint8)
+                assert np.array_equal(got, data), (container, name, chunk, d2)

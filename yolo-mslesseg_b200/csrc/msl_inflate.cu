@@ -24,6 +24,10 @@ namespace {
 
 constexpr int kInfWarps = 4;
 constexpr int kLitBits = 10, kDistBits = 8;
+constexpr int kInRing = 64;             // words (two blocks of 32: one being consumed, one prefetched)
+constexpr int kOutRing = 2048;          // bytes; matches that reach at most kRingKeep bytes back are served from shared memory
+constexpr int kFlush = 512;             // output leaves the ring in blocks of kFlush bytes
+constexpr int kRingKeep = kOutRing - 258 - 34;
 
 struct WarpTables {
     uint16_t lit[1 << kLitBits];      // (symbol << 4) | code length; 0 = code longer than kLitBits
@@ -33,6 +37,8 @@ struct WarpTables {
     int lit_count[16], dist_count[16];
     int next_code[16], offs[16];
     uint8_t lens[384];                // [0, 19): code-length code; [32, 32 + HLIT + HDIST): literal / length and distance lengths
+    uint32_t in_ring[kInRing];        // staged input words: word w of the source lives at in_ring[w % kInRing]
+    uint8_t out_ring[kOutRing];       // the last kOutRing output bytes: byte p lives at out_ring[p % kOutRing]
 };
 
 struct InfArgs {
@@ -47,16 +53,33 @@ struct InfArgs {
 
 enum { INF_OK = 0, INF_ERR_HEADER = 1, INF_ERR_BLOCK = 2, INF_ERR_CODE = 3, INF_ERR_DIST = 4, INF_ERR_SPACE = 5, INF_ERR_INPUT = 6 };
 
+// Bit reader over the warp's staged input.  The compressed bytes are read sequentially, so the warp copies them from
+// global to shared memory 32 words at a time (one coalesced load, its latency paid once per 128 bytes instead of once per
+// word on the serial decode path); refill() then costs a shared-memory read.
 struct BitReader {
     const uint32_t* w;              // src as aligned words
+    uint32_t* ring;
     unsigned long long nwords;      // words that may be read
-    unsigned long long next;        // index of the next word to load
+    unsigned long long next;        // index of the next word to move into the bit buffer
+    unsigned long long staged;      // words [.., staged) are in the ring
     unsigned long long bb;
-    int nb;
-    __device__ __forceinline__ void init(const uint8_t* src, unsigned long long src_bytes, unsigned long long bytepos) {
+    int nb, lane;
+    __device__ __forceinline__ void stage() {            // all lanes; keeps at least 8 words ahead of `next`
+        if (next + 8 >= staged) {
+            const unsigned long long i = staged + lane;
+            ring[i % kInRing] = i < nwords ? __ldg(w + i) : 0u;
+            staged += 32;
+            __syncwarp();
+        }
+    }
+    __device__ __forceinline__ void init(const uint8_t* src, unsigned long long src_bytes, unsigned long long bytepos, uint32_t* ring_, int lane_) {
         w = reinterpret_cast<const uint32_t*>(src);
+        ring = ring_; lane = lane_;
         nwords = (src_bytes + 3) >> 2;
         next = bytepos >> 2;
+        staged = next;
+        __syncwarp();
+        stage();
         bb = 0; nb = 0;
         refill();
         const int drop = (int)(bytepos & 3) * 8;
@@ -65,8 +88,8 @@ struct BitReader {
     }
     __device__ __forceinline__ void refill() {
         if (nb <= 32) {
-            const uint32_t v = next < nwords ? __ldg(w + next) : 0u;
-            bb |= (unsigned long long)v << nb;
+            stage();
+            bb |= (unsigned long long)ring[next % kInRing] << nb;
             nb += 32; ++next;
         }
     }
@@ -135,21 +158,40 @@ __global__ void __launch_bounds__(kInfWarps * 32) inflate_kernel(const InfArgs a
     const unsigned long long sbeg = a.src_off[s], send = a.src_off[s + 1];
     uint8_t* out = a.dst + a.dst_off[s];
     const unsigned long long cap = a.dst_off[s + 1] - a.dst_off[s];
-    unsigned long long pos = 0;
+    unsigned long long pos = 0, flushed = 0;          // bytes produced / bytes that left the ring for global memory
     int err = INF_OK;
     uint32_t stored_chk = 0, stored_isize = 0;
     unsigned long long bytepos = sbeg;
+    uint8_t* ring = T.out_ring;
+    const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 3) == 0;
 
-    // pending literals: one per lane, stored 32 at a time
-    int pend = 0;
-    uint32_t mylit = 0;
-    auto flush = [&]() {
-        if (pend) {
-            if (pos + pend > cap) { err = INF_ERR_SPACE; pend = 0; return; }
-            if (lane < pend) out[pos + lane] = (uint8_t)mylit;
-            pos += pend; pend = 0;
+    // Output goes to the ring first and leaves it in blocks of kFlush bytes (coalesced 32-bit stores).  The ring keeps the
+    // last kOutRing bytes, flushed or not, so near matches never touch global memory.
+    auto flush_blocks = [&]() {
+        while (pos - flushed >= kFlush) {
             __syncwarp();
+            const unsigned mis = (unsigned)(flushed & 3);
+            if (mis || !out_aligned) {
+                // realign (after a stored block the flushed count is arbitrary); unaligned outputs go byte by byte
+                const unsigned nbyte = out_aligned ? 4u - mis : (unsigned)kFlush;
+                for (unsigned k = lane; k < nbyte; k += 32) out[flushed + k] = ring[(flushed + k) % kOutRing];
+                flushed += nbyte;
+                continue;
+            }
+            const uint32_t* r32 = reinterpret_cast<const uint32_t*>(ring);
+            uint32_t* o32 = reinterpret_cast<uint32_t*>(out + flushed);
+            const unsigned w0 = (unsigned)(flushed % kOutRing) >> 2;
+#pragma unroll
+            for (int k = 0; k < kFlush / 128; ++k) o32[k * 32 + lane] = r32[(w0 + k * 32 + lane) % (kOutRing / 4)];
+            flushed += kFlush;
         }
+    };
+    auto flush_all = [&]() {
+        flush_blocks();
+        __syncwarp();
+        for (unsigned long long k = flushed + lane; k < pos; k += 32) out[k] = ring[k % kOutRing];
+        flushed = pos;
+        __syncwarp();
     };
 
     for (;;) {      // members (gzip files may hold several)
@@ -171,26 +213,41 @@ __global__ void __launch_bounds__(kInfWarps * 32) inflate_kernel(const InfArgs a
             bytepos = p;
         }
         BitReader br;
-        br.init(a.src, a.src_bytes, bytepos);
+        br.init(a.src, a.src_bytes, bytepos, T.in_ring, lane);
         bool fixed_ready = false;
         // ---- blocks
         for (;;) {
             br.refill();
             const uint32_t bfinal = br.take(1), btype = br.take(2);
             if (btype == 0) {
-                // stored: skip to the byte boundary, LEN, NLEN, then a warp copy
+                // stored: skip to the byte boundary, LEN, NLEN, then the bytes pass through the ring like everything else
                 unsigned long long bp = (br.bitpos() + 7) >> 3;
                 if (bp + 4 > send) { err = INF_ERR_INPUT; break; }
                 const uint32_t len = a.src[bp] | ((uint32_t)a.src[bp + 1] << 8), nlen = a.src[bp + 2] | ((uint32_t)a.src[bp + 3] << 8);
                 if ((len ^ nlen) != 0xffffu) { err = INF_ERR_BLOCK; break; }
                 bp += 4;
                 if (bp + len > send) { err = INF_ERR_INPUT; break; }
-                flush();
-                if (err || pos + len > cap) { err = INF_ERR_SPACE; break; }
-                for (uint32_t i = lane; i < len; i += 32) out[pos + i] = a.src[bp + i];
-                __syncwarp();
+                if (pos + len > cap) { err = INF_ERR_SPACE; break; }
+                // what is still in the ring leaves first; then the block goes straight from the source to the output (four
+                // independent byte loads per lane in flight) and its last kOutRing bytes also into the ring, for later matches
+                flush_all();
+                for (uint32_t base = 0; base < len; base += 128) {
+                    uint32_t v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { const uint32_t i = base + lane + 32 * k; v[k] = i < len ? a.src[bp + i] : 0u; }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t i = base + lane + 32 * k;
+                        if (i < len) {
+                            out[pos + i] = (uint8_t)v[k];
+                            if (len - i <= (uint32_t)kOutRing) ring[(pos + i) % kOutRing] = (uint8_t)v[k];
+                        }
+                    }
+                }
                 pos += len;
-                br.init(a.src, a.src_bytes, bp + len);
+                flushed = pos;
+                __syncwarp();
+                br.init(a.src, a.src_bytes, bp + len, T.in_ring, lane);
             } else if (btype == 3) {
                 err = INF_ERR_BLOCK; break;
             } else {
@@ -239,7 +296,7 @@ __global__ void __launch_bounds__(kInfWarps * 32) inflate_kernel(const InfArgs a
                     }
                     if (bad) { err = INF_ERR_BLOCK; break; }
                     __syncwarp();
-                    // lens[32 ..): literal / length lengths, then distance lengths (moved down so that both tables index from 0)
+                    // lens[32 ..): literal / length lengths, then distance lengths
                     build_table(T.lens + 32, hlit, T.lit, kLitBits, T.lit_count, T.lit_sorted, T.codes, T.next_code, T.offs, lane);
                     build_table(T.lens + 32 + hlit, hdist, T.dist, kDistBits, T.dist_count, T.dist_sorted, T.codes, T.next_code, T.offs, lane);
                 }
@@ -249,11 +306,10 @@ __global__ void __launch_bounds__(kInfWarps * 32) inflate_kernel(const InfArgs a
                     const int sym = decode_sym(br, T.lit, kLitBits, T.lit_count, T.lit_sorted);
                     if (sym < 256) {
                         if (sym < 0) { err = INF_ERR_CODE; break; }
-                        if (lane == pend) mylit = (uint32_t)sym;
-                        if (++pend == 32) {
-                            flush();
-                            if (err) break;
-                        }
+                        if (pos >= cap) { err = INF_ERR_SPACE; break; }
+                        if (lane == 0) ring[pos % kOutRing] = (uint8_t)sym;
+                        ++pos;
+                        if (pos - flushed >= kFlush) flush_blocks();
                         continue;
                     }
                     if (sym == 256) break;
@@ -265,29 +321,37 @@ __global__ void __launch_bounds__(kInfWarps * 32) inflate_kernel(const InfArgs a
                     if (ds < 0 || ds > 29) { err = INF_ERR_CODE; break; }
                     br.refill();
                     const unsigned dist = (unsigned)kDistBase[ds] + br.take(kDistExtra[ds]);
-                    if (pos + pend + len > cap) { err = INF_ERR_SPACE; break; }
-                    flush();
-                    if (err) break;
+                    if (pos + len > cap) { err = INF_ERR_SPACE; break; }
                     if (dist > pos) { err = INF_ERR_DIST; break; }
-                    const uint8_t* from = out + pos - dist;
-                    if (dist >= (unsigned)len) {
-                        for (int i = lane; i < len; i += 32) out[pos + i] = from[i];
-                    } else if (dist == 1) {
-                        const uint8_t v = from[0];
-                        for (int i = lane; i < len; i += 32) out[pos + i] = v;
+                    __syncwarp();                                   // literals written by lane 0 are visible to every lane
+                    const unsigned long long from = pos - dist;
+                    if (dist + (unsigned)len <= (unsigned)kRingKeep) {
+                        // the whole source lies in the ring
+                        if (dist == 1) {
+                            const uint8_t v = ring[from % kOutRing];
+                            for (int i = lane; i < len; i += 32) ring[(pos + i) % kOutRing] = v;
+                        } else if (dist >= (unsigned)len) {
+                            for (int i = lane; i < len; i += 32) ring[(pos + i) % kOutRing] = ring[(from + i) % kOutRing];
+                        } else {
+                            for (int i = lane; i < len; i += 32) ring[(pos + i) % kOutRing] = ring[(from + (unsigned)i % dist) % kOutRing];
+                        }
                     } else {
-                        for (int i = lane; i < len; i += 32) out[pos + i] = from[(unsigned)i % dist];
+                        // far match: bytes older than the ring's guaranteed window come from global memory (they were flushed:
+                        // at most kFlush + 290 bytes are ever unflushed, less than kRingKeep)
+                        for (int i = lane; i < len; i += 32) {
+                            const unsigned long long idx = from + (dist >= (unsigned)len ? (unsigned)i : (unsigned)i % dist);
+                            ring[(pos + i) % kOutRing] = (pos - idx <= (unsigned long long)kRingKeep) ? ring[idx % kOutRing] : out[idx];
+                        }
                     }
                     __syncwarp();
                     pos += len;
+                    if (pos - flushed >= kFlush) flush_blocks();
                 }
                 if (err) break;
             }
             if (br.bitpos() > send * 8ull) { err = INF_ERR_INPUT; break; }
             if (bfinal) { bytepos = (br.bitpos() + 7) >> 3; break; }
         }
-        if (err) break;
-        flush();
         if (err) break;
         // ---- trailer
         if (a.container == MSL_Z_ZLIB) {
@@ -304,6 +368,7 @@ __global__ void __launch_bounds__(kInfWarps * 32) inflate_kernel(const InfArgs a
         }
         break;
     }
+    flush_all();
     if (lane == 0) {
         uint32_t* st = a.status + 4 * (size_t)s;
         st[0] = (uint32_t)err; st[1] = (uint32_t)pos; st[2] = stored_chk; st[3] = stored_isize;
@@ -334,6 +399,63 @@ __global__ void __launch_bounds__(128) png_unfilter_kernel(const PngArgs2 a) {
     uint8_t* out = a.out + (size_t)s * a.H * a.W;
     if (have < (unsigned long long)a.H * (rb + 1)) { if (lane == 0) a.status[s] = 1; return; }
     uint32_t bad = 0;
+    if (bpp == 1 && rb <= 256) {
+        // 8-bit gray scanlines of up to 256 bytes (the predicted masks cv2.imwrite saves): every lane keeps bytes lane, lane + 32,
+        // ... of the current and of the previous (reconstructed) scanline in registers and the next scanline's loads are issued
+        // before the current one is processed, so a row costs one memory round trip at most and no row is read twice
+        uint32_t cur[8], up[8], nxt[8];
+        int ft = raw[0], ft_next = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int i = lane + 32 * k; up[k] = 0; cur[k] = i < rb ? raw[1 + i] : 0u; }
+        for (int y = 0; y < a.H; ++y) {
+            if (y + 1 < a.H) {
+                const uint8_t* nr = raw + (size_t)(y + 1) * (rb + 1);
+                ft_next = nr[0];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const int i = lane + 32 * k; nxt[k] = i < rb ? nr[1 + i] : 0u; }
+            }
+            if (ft == 1) {              // Sub: prefix sums mod 256 along the scanline
+                int carry = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (32 * k < rb) {
+                        const int v = warp_incl_scan((int)cur[k], lane) + carry;
+                        cur[k] = (uint32_t)v & 0xffu;
+                        carry = __shfl_sync(FULL, v, 31) & 0xff;
+                    }
+                }
+            } else if (ft == 2) {       // Up
+#pragma unroll
+                for (int k = 0; k < 8; ++k) cur[k] = (cur[k] + up[k]) & 0xffu;
+            } else if (ft == 3 || ft == 4) {
+                // Average / Paeth: every byte needs its reconstructed left neighbour - serial along the scanline, the
+                // neighbour handed from lane to lane
+                int left = 0, upleft = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (32 * k < rb) {
+                        for (int l = 0; l < 32; ++l) {
+                            const int u = (int)up[k];
+                            int v = (int)cur[k];
+                            if (lane == l) v = (v + (ft == 3 ? ((left + u) >> 1) : paeth(left, u, upleft))) & 0xff;
+                            cur[k] = (uint32_t)v;
+                            left = __shfl_sync(FULL, v, l);
+                            upleft = __shfl_sync(FULL, u, l);
+                        }
+                    }
+                }
+            } else if (ft != 0) bad = 1;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = lane + 32 * k;
+                if (i < rb) out[(size_t)y * a.W + i] = (uint8_t)cur[k];
+                up[k] = cur[k]; cur[k] = nxt[k];
+            }
+            ft = ft_next;
+        }
+        if (lane == 0) a.status[s] = bad;
+        return;
+    }
     for (int y = 0; y < a.H; ++y) {
         uint8_t* cur = raw + (size_t)y * (rb + 1) + 1;
         const uint8_t* up = y ? cur - (rb + 1) : nullptr;

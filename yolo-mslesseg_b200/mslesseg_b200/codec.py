@@ -26,7 +26,7 @@ import torch
 from . import _lib as L
 from . import ops
 
-CHUNK = 65536
+CHUNK = 16384          # payload bytes per gzip member of the files written here (one deflate tile, one decoder lane)
 _NIFTI_DT = {2: ("u1", 1), 4: ("i2", 2), 8: ("i4", 4), 16: ("f4", 4), 64: ("f8", 8), 256: ("i1", 1), 512: ("u2", 2), 768: ("u4", 4)}
 _NIFTI_CODE = {"uint8": 2, "int16": 4, "int32": 8, "float32": 16, "float64": 64, "int8": 256, "uint16": 512, "uint32": 768}
 _INF_ERR = {1: "bad container header", 2: "bad block", 3: "bad Huffman code", 4: "distance too far back", 5: "output does not fit",

@@ -438,7 +438,7 @@ class PackedStreams:
 def deflate_chunks(src: torch.Tensor, chunk_len: int = 65536, container: str = "gzip", dist2: int = 0,
                    out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> PackedStreams:
     """Cuts the bytes of `src` (any contiguous CUDA tensor) into chunks of chunk_len bytes and deflates every chunk into
-    its own stream (container "raw", "zlib" or "gzip").  The concatenation of the gzip members is a valid .gz file of the
+    its own stream (container "raw", "zlib" or "gzip"; dist2 = the match distance 1..4, 0 = 1: the element size in bytes).  The concatenation of the gzip members is a valid .gz file of the
     whole buffer (reference utils/utils.py:176-177 nib.save -> gzip)."""
     _need_cuda(src, "src")
     lib = L.load()
