@@ -579,6 +579,8 @@ def run_e2e(args, torch, dist, ops, S, device, world, flair, gt, preds):
                 if count:
                     d2h += moved
 
+    d2h_events = None        # profile pass: CUDA events around every chunk's device-to-host copies
+
     def e2e_step(count=False):
         chunks = list(enumerate(range(0, B, CH)))
         for i, (ci, c0) in enumerate(chunks):
@@ -688,8 +690,9 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
              "rvol": {pl: torch.empty((CH, Z, Y, X), dtype=torch.uint8, device=device) for pl in PLANOS},
              "event": torch.cuda.Event(), "done": torch.cuda.Event()}
         d["outs4"] = {pl: torch.empty((4, CH, dims[pl][0], dims[pl][2], dims[pl][1]), dtype=torch.uint8, device=device) for pl in PLANOS}
-        d["in_p"] = {pl: torch.empty(max_pr[pl], dtype=torch.uint8, device=device) for pl in PLANOS}
-        d["raw_p"] = {pl: torch.empty(max_ps[pl] * ((dims[pl][1] * (dims[pl][2] + 1) + 15) & ~15) + 64, dtype=torch.uint8, device=device) for pl in PLANOS}
+        # the PNG files of the three planes share one buffer (and one inflate launch per chunk)
+        d["in_p"] = torch.empty(sum((max_pr[pl] + 15) & ~15 for pl in PLANOS) + 64, dtype=torch.uint8, device=device)
+        d["raw_p"] = torch.empty(sum(max_ps[pl] * ((dims[pl][1] * (dims[pl][2] + 1) + 15) & ~15) for pl in PLANOS) + 64, dtype=torch.uint8, device=device)
         d["pred"] = {pl: torch.empty((max_ps[pl], dims[pl][1], dims[pl][2]), dtype=torch.uint8, device=device) for pl in PLANOS}
         npng = {pl: 4 * CH * dims[pl][0] for pl in PLANOS}
         rawpng = {pl: dims[pl][2] * (dims[pl][1] + 1) for pl in PLANOS}
@@ -768,26 +771,34 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
                 ops.enhance_volumes(fl, MEJORAS, PLANOS, outs=o, workspace=d["ws"])
             else:
                 o = ops.enhance_volumes(fl, MEJORAS, PLANOS, workspace=d["ws"])
-            # ---- predicted-mask PNGs: file bytes up, inflate, unfilter, stack into volumes
+            # ---- predicted-mask PNGs: file bytes up, ONE inflate launch for the three planes, then unfilter + stack per plane
+            so_all, do_all, per_plane = [], [], {}
+            in_base = raw_base = nstr = 0
             for pl in PLANOS:
                 a, b = ranges[pl][ci]
                 fa, fb = int(HP[pl].off[a]), int(HP[pl].off[b])
-                d["in_p"][pl][:fb - fa].copy_(HP[pl].buf[fa:fb], non_blocking=True)
-                tab = codec.png_table(HP[pl].np, HP[pl].off[a:b + 1])
-                w, h, bpp, istart, ilen = tab
-                rawsz = h * (w * bpp + 1)
-                rp = (rawsz + 15) & ~15
-                so = np.concatenate([istart - fa, [istart[-1] - fa + ilen[-1]]]).astype(np.int64)   # stream i ends where i+1 starts: the chunk tails (CRC, IEND, next header) are ignored by the zlib reader
-                do = (np.arange(b - a + 1, dtype=np.int64) * rp)
-                so_d, do_d = torch.from_numpy(so).to(device, non_blocking=True), torch.from_numpy(do).to(device, non_blocking=True)
-                codec.inflate_device(d["in_p"][pl], so_d, d["raw_p"][pl], do_d, "zlib", status=d["status"][srow:srow + (b - a)])
-                srow += b - a
+                d["in_p"][in_base:in_base + fb - fa].copy_(HP[pl].buf[fa:fb], non_blocking=True)
+                w, h, bpp, istart, ilen = codec.png_table(HP[pl].np, HP[pl].off[a:b + 1])
+                rp = (h * (w * bpp + 1) + 15) & ~15
+                so_all.append(istart - fa + in_base)      # stream i ends where i+1 starts: the chunk tails (CRC, IEND, next header) are ignored by the zlib reader
+                do_all.append(raw_base + np.arange(b - a, dtype=np.int64) * rp)
+                per_plane[pl] = (a, b, h, w, bpp, nstr)
+                nstr += b - a
+                in_base += (fb - fa + 15) & ~15
+                raw_base += (b - a) * rp
+                nb += (fb - fa) + 2 * 8 * (b - a) + 8 * (b - a)
+            so = np.concatenate(so_all + [np.asarray([in_base], np.int64)]).astype(np.int64)
+            do = np.concatenate(do_all + [np.asarray([raw_base], np.int64)]).astype(np.int64)
+            so_d, do_d = torch.from_numpy(so).to(device, non_blocking=True), torch.from_numpy(do).to(device, non_blocking=True)
+            codec.inflate_device(d["in_p"], so_d, d["raw_p"], do_d, "zlib", status=d["status"][srow:srow + nstr])
+            srow += nstr
+            for pl in PLANOS:
+                a, b, h, w, bpp, s0 = per_plane[pl]
                 pred = d["pred"][pl][:b - a]
-                codec.png_unfilter_device(d["raw_p"][pl], do_d, h, w, bpp, pred)
+                codec.png_unfilter_device(d["raw_p"], do_d[s0:s0 + (b - a) + 1], h, w, bpp, pred)
                 vs = torch.from_numpy(pred_vs[pl][a:b] - c0).to(device, non_blocking=True)
                 ix = torch.from_numpy(pred_ix[pl][a:b]).to(device, non_blocking=True)
                 ops.recon(pred, vs, ix, pl, n, S.SHAPE_XYZ, out=d["rvol"][pl][:n])
-                nb += (fb - fa) + so.nbytes + do.nbytes + 8 * (b - a)
             cons, counts = ops.consensus_eval(d["rvol"]["axial"][:n], d["rvol"]["coronal"][:n], d["rvol"]["sagital"][:n], g, 2)
             h_counts[c0:c0 + n].copy_(counts, non_blocking=True)
             # ---- results: PNG files of the 12 stacks, .nii.gz of the three reconstructions (float32) and the consensus (uint8)
@@ -822,6 +833,9 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
         tot = d["h_tot"].numpy()
         with torch.cuda.stream(st):
             moved = 0
+            if d2h_events is not None:
+                d2h_events.append([torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), 0])
+                d2h_events[-1][0].record(st)
             for k, pl in enumerate(PLANOS):
                 t = int(tot[k])
                 h_png[pl][hi][:t].copy_(res[pl].data[:t], non_blocking=True)
@@ -841,8 +855,13 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
             n_status[hi] = srow
             moved += t + res["gz8"].off.numel() * 8 + srow * 16 + 16
             d["done"].record(st)
+            if d2h_events is not None:
+                d2h_events[-1][1].record(st)
+                d2h_events[-1][2] = moved
             if count:
                 d2h += moved
+
+    d2h_events = None        # profile pass: CUDA events around every chunk's device-to-host copies
 
     def e2e_step(count=False):
         chunks = list(enumerate(range(0, B, CH)))
@@ -876,9 +895,24 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
     host_enqueue_ms = host_total_ms - waits[0] * 1e3          # Python + launch work of one step (unprofiled)
     sync_all()
     _L2.profile_enable(True)
+    d2h_events = []
     e2e_step()
     sync_all()
+    d2h_ms = sum(a_.elapsed_time(b_) for a_, b_, _ in d2h_events)
+    d2h_gbs = sum(m_ for _, _, m_ in d2h_events) / max(d2h_ms, 1e-9) / 1e6
+    d2h_events = None
+    tl = _L2.profile_timeline()
     kern = {k: round(v[0], 3) for k, v in sorted(_L2.profile_collect().items(), key=lambda kv: -kv[1][0])}
+    # union of the kernel intervals of that step = time during which at least one of this library's kernels was running
+    busy, end = 0.0, -1.0
+    for _, _, a_, b_ in sorted(tl, key=lambda r: r[2]):
+        if b_ > end:
+            busy += b_ - max(a_, end)
+            end = b_
+    span = (max(r[3] for r in tl) - min(r[2] for r in tl)) if tl else 0.0
+    if os.environ.get("MSL_BENCH_TIMELINE"):
+        with open(os.environ["MSL_BENCH_TIMELINE"], "w") as f:
+            json.dump(tl, f)
     # ---- the host files decode (Pillow / gzip on the host = checker) to what the device holds for the last chunks
     import gzip as _gz
     import io as _io
@@ -915,7 +949,7 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
     return {"value": world * B * N_VOX / sec / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "ms_per_step": sec * 1e3, "steps": K, "host_results_equal_device": bool(ok),
             "uncompressed_bytes_per_step": {"inputs": int(raw_in), "results": int(raw_out)},
-            "kernel_ms_per_step": kern, "host_enqueue_ms_per_step": host_enqueue_ms,
+            "kernel_ms_per_step": kern, "d2h_copy_ms_per_step": round(d2h_ms, 3), "d2h_copy_gb_s": round(d2h_gbs, 1), "kernel_busy_ms_per_step": round(busy, 3), "kernel_span_ms_per_step": round(span, 3), "host_enqueue_ms_per_step": host_enqueue_ms,
             "note": ("host buffers hold FILES: .nii.gz volumes (FLAIR float32, GT float32) and predicted-mask PNGs in; PNG slices of the 12 "
                      "stacks, float32 .nii.gz of the 3 reconstructions, uint8 consensus .nii.gz and the count table out; inflate / "
                      "deflate on the GPU; 4-patient chunks over 3 streams; wall clock around synchronised steps")}

@@ -315,11 +315,14 @@ int msl_slice_counts(const uint8_t* gt, const uint8_t* pred, int nvol, int X, in
  * msl_kernel_launches: kernels launched by this library since load (total; per kind if non-NULL,
  * array of msl_kernel_kinds() entries).  msl_profile_enable(1) makes every launch record a pair of
  * CUDA events on its stream; msl_profile_collect synchronises them, returns milliseconds and launch
- * counts per kind and switches profiling off.  bench.py uses it for the roofline line. */
+ * counts per kind and switches profiling off.  bench.py uses it for the roofline line.
+ * msl_profile_timeline (before the collect): up to `cap` recorded launches in launch order - kind, stream
+ * handle, start and end in milliseconds after the first recorded launch; returns the count (-1: error). */
 int                msl_kernel_kinds(void);
 const char*        msl_kernel_name(int kind);
 unsigned long long msl_kernel_launches(unsigned long long* per_kind);
 int                msl_profile_enable(int on);
+int                msl_profile_timeline(int cap, int* kind, unsigned long long* stream, double* start_ms, double* end_ms);
 int                msl_profile_collect(double* ms_per_kind, unsigned long long* n_per_kind);
 
 #ifdef __cplusplus

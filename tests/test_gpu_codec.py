@@ -1,6 +1,7 @@
 """GPU: the device byte-stream codec (msl_codec.cu / msl_inflate.cu) against zlib, gzip and Pillow on the host."""
 import gzip
 import io
+import struct
 import zlib
 
 import numpy as np
@@ -176,6 +177,23 @@ def test_png_decode_first_channel(ops, codec, cuda_device):
             imgs.append(arr if bpp == 1 else arr[..., 0])
         got = codec.png_decode_first_channel(files, cuda_device).cpu().numpy()
         assert np.array_equal(got, np.stack(imgs)), mode
+    # hand-built files: noise images, a random None / Sub / Up filter per scanline (the row-parallel path; 257 columns: serial)
+    def png_of(img, fts):
+        rows = []
+        for y, ft in enumerate(fts):
+            cur = img[y].astype(np.int16)
+            ref = np.zeros_like(cur) if ft == 0 else (np.concatenate([[0], cur[:-1]]) if ft == 1 else (img[y - 1].astype(np.int16) if y else np.zeros_like(cur)))
+            rows.append(bytes([ft]) + ((cur - ref) & 0xff).astype(np.uint8).tobytes())
+        def chunk(t, d):
+            return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d))
+        h, w = img.shape
+        return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 0, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"".join(rows), 6))
+                + chunk(b"IEND", b""))
+    for w in (182, 256, 257, 31):
+        imgs = rng.integers(0, 256, (5, 73, w), dtype=np.uint8)
+        files = [png_of(im, rng.integers(0, 3, 73) if k else np.full(73, 2)) for k, im in enumerate(imgs)]
+        assert np.array_equal(np.asarray(Image.open(io.BytesIO(files[1]))), imgs[1])
+        assert np.array_equal(codec.png_decode_first_channel(files, cuda_device).cpu().numpy(), imgs), w
     # our own encoder's files
     px = torch.from_numpy(masks).to(cuda_device)
     assert np.array_equal(codec.png_decode_first_channel(ops.png_encode(px).files(), cuda_device).cpu().numpy(), masks)

@@ -296,10 +296,17 @@ def test_uint8_images_and_degenerate_inputs(ops, torch_mod, cuda_device):
     # empty slice list
     vol = torch.zeros((1, 8, 8, 8), dtype=torch.float32, device=cuda_device)
     assert ops.enhance_slices(vol, "GC", "axial", [], []).shape == (0, 8, 8)
-    # out-of-range entries are skipped (their output stays untouched)
+    # out-of-range entries: host lists raise like the reference's slice access does; index tensors that live on the device are
+    # not inspected - the kernel skips such pairs (a given `out` stays untouched there, a fresh one comes back zeroed)
     out = torch.full((2, 8, 8), 7, dtype=torch.uint8, device=cuda_device)
-    ops.enhance_slices(vol, "GC", "axial", [0, 0], [3, 99], out=out)
+    with pytest.raises(IndexError):
+        ops.enhance_slices(vol, "GC", "axial", [0, 0], [3, 99], out=out)
+    dv = torch.tensor([0, 0], dtype=torch.int32, device=cuda_device)
+    di = torch.tensor([3, 99], dtype=torch.int32, device=cuda_device)
+    ops.enhance_slices(vol, "GC", "axial", dv, di, out=out)
     assert int(out[0].max()) == 0 and int(out[1].min()) == 7
+    fresh = ops.enhance_slices(vol + 1.0, "LT", "axial", dv, di)
+    assert int(fresh[1].max()) == 0
 
 
 def test_lesion_slices_golden(ops, torch_mod, golden, cuda_device):

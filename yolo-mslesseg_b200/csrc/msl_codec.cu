@@ -7,15 +7,18 @@
 // deflate_kernel: one CTA per stream (a PNG image, or a 16 KB chunk of a NIfTI file).  Data on this path is either
 //   incompressible for a fixed Huffman code (enhanced brain tissue: 8 - 9 bits per literal byte) or one long run
 //   (skull-stripped background, masks, padding), so the stream is built from two kinds of blocks decided per WARP:
-//   a tile of 16 KB is cut into 256 segments of 64 bytes, one per thread; a byte-SIMD compare gives each thread the mask
-//   x[i] == x[i - d] (d = 1: repeated bytes, 4: repeated RGBA pixels / float32 voxels); a ballot tells the warp which of its
-//   32 segments are entirely inside a run.  Every maximal group of neighbouring run segments becomes ONE fixed-Huffman
-//   block holding a few 258-byte matches (13 bits each); every group of other segments becomes ONE stored block (raw
-//   bytes, byte aligned).  A warp's output is therefore whole bytes (a trailing fixed block is realigned by an empty stored
-//   block), sizes are known from the ballot alone, a block scan places the warps, the headers / matches are written by
-//   lane 0 and the stored bytes are copied by the warp.  No literal is ever Huffman-coded - neither here nor in the decoder,
-//   which meets ~10 symbols per 2 KB instead of 2,000.  Staging area, 16-byte flushes, carry to the next tile, Adler-32 /
-//   CRC-32 of the raw bytes and the container header / trailer are handled by the same CTA.
+//   a tile of 4 KB is cut into 256 segments of 16 bytes, one per thread, held in four registers; a byte-SIMD compare gives
+//   each thread the mask x[i] == x[i - d] (d = 1: repeated bytes, 4: repeated RGBA pixels / float32 voxels); a ballot tells
+//   the warp which of its 32 segments are entirely inside a run.  Every maximal group of neighbouring run segments becomes
+//   ONE fixed-Huffman block of one or two matches (looked up in a 32-entry table built per launch); every group of other
+//   segments becomes ONE stored block (raw bytes, byte aligned).  A warp's output is therefore whole bytes (a fixed block is
+//   realigned by the header of the stored block behind it, an empty one at the end of the warp), sizes are known from the
+//   ballot alone, a warp scan + block scan places every lane, headers are written by the lanes that start a block and every
+//   literal lane copies its own 16 bytes.  No literal is ever Huffman-coded - neither here nor in the decoder, which meets
+//   a handful of symbols per 512 bytes.  The next tile is loaded while this one is encoded (image mode: aligned words,
+//   funnel-shifted, the filter byte shifted in), two staging buffers alternate so that a tile costs three barriers;
+//   16-byte flushes, the carry to the next tile, Adler-32 (dp4a) / CRC-32 (slicing by four from registers + one GF(2)
+//   multiplication per thread) of the raw bytes and the container header / trailer are handled by the same CTA.
 // scan_sizes_kernel + pack_kernel: the variable-length streams are packed back to back (exclusive scan of the sizes) into
 //   one buffer = one D2H copy; PNG's IDAT CRC-32 (over the compressed bytes) is computed during the copy.
 #include <cstring>
@@ -75,33 +78,14 @@ struct ZArgs {
     size_t slot_pitch;
     uint32_t* meta;            // [n][4]: container bytes in the slot, raw bytes, checksum of the raw bytes, offset of the IDAT chunk type
     uint32_t crcP[kZThreads];  // x^(8 * kSeg * k): what a thread's 16-byte CRC is multiplied by when k segments follow it in the tile
-    uint32_t crc_tile;         // x^(8 * kTile)
-    uint32_t crc_part_len[2], crc_part_mul[2];   // x^(8 * t) for the partial-tile lengths t known on the host (0 = unused)
+    uint32_t crc_tilek[4];     // x^(8 * kTile * (k + 1)): k + 1 all-zero tiles
+    const uint8_t* tmpl;       // plain mode: the stream of one full all-zero chunk ([0, 16): its meta row, [16, ..): its bytes), or NULL
+    int zero_source;           // the launch that builds the template: every raw byte reads as zero
 };
 
 __device__ __forceinline__ unsigned hdr_len_of(int container) {
     return (0x2b180200u >> (8 * (container & 3))) & 0xffu;       // raw 0, zlib 2, gzip 24, PNG 43 (no jump table)
 }
-
-// ---- bit writer into the zeroed staging area (LSB-first, RFC 1951 section 3.1.1)
-struct BitWriter {
-    uint32_t* y;          // staging words
-    unsigned long long acc;
-    int nacc;             // valid bits in acc (the first nacc0 of them are zeros standing for another thread's bits)
-    unsigned word;
-    bool first;
-    __device__ __forceinline__ void init(uint32_t* y_, unsigned bitpos) { y = y_; acc = 0; nacc = (int)(bitpos & 31u); word = bitpos >> 5; first = true; }
-    __device__ __forceinline__ void put(uint32_t v, int n) {
-        acc |= (unsigned long long)v << nacc;
-        nacc += n;
-        if (nacc >= 32) {
-            if (first) { atomicOr(&y[word], (uint32_t)acc); first = false; }
-            else y[word] = (uint32_t)acc;
-            acc >>= 32; nacc -= 32; ++word;
-        }
-    }
-    __device__ __forceinline__ void finish() { if (nacc > 0 && (uint32_t)acc) atomicOr(&y[word], (uint32_t)acc); }
-};
 
 __device__ __forceinline__ uint32_t rev_bits(uint32_t v, int n) { return __brev(v) >> (32 - n); }
 
@@ -113,9 +97,8 @@ __device__ __forceinline__ int fixed_litlen(uint32_t sym, uint32_t& code) {
     code = rev_bits(0xc0 + (sym - 280), 8); return 8;
 }
 
-// cost in bits / emission of one match (length 3..258, distance 1..32768)
-template <bool EMIT>
-__device__ __forceinline__ int put_match(BitWriter& bw, int len, int dist) {
+// One match of `len` bytes (3..258) at distance d (1..4: distance codes 0..3, no extra bits): its bits, LSB first
+__device__ __forceinline__ int match_bits(int len, int d, uint32_t& pat) {
     uint32_t sym, eb = 0, ev = 0;
     if (len == 258) sym = 285;
     else {
@@ -123,19 +106,25 @@ __device__ __forceinline__ int put_match(BitWriter& bw, int len, int dist) {
         if (l < 8) sym = 257 + l;
         else { eb = 29 - __clz(l); sym = 257 + 4 * (eb + 1) + ((l >> eb) & 3); ev = l & ((1u << eb) - 1); }
     }
-    const uint32_t D = (uint32_t)dist - 1;
-    uint32_t dcode, deb = 0, dev = 0;
-    if (D < 4) dcode = D;
-    else { deb = 30 - __clz(D); dcode = 2 * (deb + 1) + ((D >> deb) & 1); dev = D & ((1u << deb) - 1); }
     uint32_t code;
     const int n = fixed_litlen(sym, code);
-    if (EMIT) {
-        bw.put(code, n);
-        if (eb) bw.put(ev, (int)eb);
-        bw.put(rev_bits(dcode, 5), 5);
-        if (deb) bw.put(dev, (int)deb);
-    }
-    return n + (int)eb + 5 + (int)deb;
+    pat = code | (ev << n) | (rev_bits((uint32_t)d - 1, 5) << (n + (int)eb));
+    return n + (int)eb + 5;
+}
+
+// A run of 16 * (k + 1) bytes (k = 0..31: whole segments of one warp) as ONE fixed-Huffman block: header (BFINAL 0, BTYPE 01),
+// one or two matches (258 + the rest: the rest of a multiple of 16 is never 1 or 2), end of block.  Bits 0..47 hold the
+// block LSB first, bits 48..55 its length in bits (at most 3 + 13 + 18 + 7).
+__device__ __forceinline__ unsigned long long run_block(int k, int d) {
+    const int bytes = kSeg * (k + 1);
+    unsigned long long acc = 2u;
+    int n = 3;
+    uint32_t pat;
+    if (bytes >= 258 + 3) { const int m = match_bits(258, d, pat); acc |= (unsigned long long)pat << n; n += m; }
+    const int rest = bytes >= 258 + 3 ? bytes - 258 : bytes;
+    { const int m = match_bits(rest, d, pat); acc |= (unsigned long long)pat << n; n += m; }
+    n += 7;
+    return acc | ((unsigned long long)n << 48);
 }
 
 // Tile bytes in shared memory: logical index i (>= -64) lives at i + 4 * ((i + 64) / 64): every thread's 64-byte segment
@@ -181,91 +170,93 @@ __device__ __forceinline__ SegMasks seg_masks(const uint8_t* X, int beg, int end
     return m;
 }
 
-// `bytes` (a multiple of 64, at most 2048) of one run as matches of up to 258 bytes: returns the bits, emits when EMIT
-template <bool EMIT>
-__device__ __forceinline__ int put_run(BitWriter& bw, int bytes, int d) {
-    int bits = 0;
-    while (bytes > 0) {
-        int take = bytes < 258 ? bytes : 258;
-        if (bytes - take > 0 && bytes - take < 3) take -= 3;       // (cannot happen for multiples of 64; kept for safety)
-        bits += put_match<EMIT>(bw, take, d);
-        bytes -= take;
-    }
-    return bits;
-}
-
-// ---- one warp's 32 segments as blocks, every lane working for itself
-// Blocks alternate between the two kinds, and a stored block ends on a byte boundary, so every fixed block STARTS on one (at
-// the warp's first byte or behind a stored block).  That makes every size local: the lane that starts a fixed block emits the
-// block and the header of whatever stored block follows it (an empty one at the end of the warp) - whole bytes; the lane that
-// starts a stored block emits a header only if it opens the warp, and accounts for the block's bytes.  A warp scan of those
-// sizes gives every lane its place; headers are written by their lanes in parallel, and every literal lane copies its own
-// 16 bytes.
+// ---- a tile's 256 segments as blocks, every lane working for itself
+// A maximal group of literal segments becomes ONE stored block (up to the whole 4 KB tile, across warps); run segments become
+// one fixed-Huffman block per warp and group.  A stored block ends on a byte boundary, so every fixed block STARTS on one (at
+// the tile's first byte, behind a stored block, or behind the empty stored block that closes the previous fixed block).  That
+// makes every size local: the lane that starts a fixed block emits the block and the header of the stored block behind it (an
+// empty one when another fixed block or the end of the tile follows) - whole bytes; a literal lane accounts for its own bytes,
+// plus a header if it opens the tile.  A scan of those sizes gives every lane its place; headers are written by their lanes in
+// parallel, and every literal lane copies its own 16 bytes.
 struct LanePlan {
-    bool start, run;
+    bool start, run, hdr;
     int bytes;        // bytes of the block this lane starts
-    int next_bytes;   // bytes of the stored block that follows this lane's fixed block (0: none, an empty one is emitted)
+    int next_bytes;   // bytes of the stored block that follows this lane's fixed block (0: an empty one is emitted)
     int hbits;        // bits of the fixed block (header + matches + end of block)
-    int size;         // bytes this lane contributes to the warp's output
+    int size;         // bytes this lane contributes to the tile's output
 };
 
-__device__ __forceinline__ LanePlan lane_plan(unsigned run_mask, int nact, int wbytes, int d, int lane) {
+// bytes of the literal group that starts at segment e of the tile (0 when that segment is a run or behind the end)
+__device__ __forceinline__ int literal_group_bytes(const unsigned* tile_runs, int e, int nseg, unsigned tn) {
+    int s = e;
+    while (s < nseg) {
+        const int b = s & 31;
+        const unsigned x = ~tile_runs[s >> 5] >> b;                    // literal segments from s on, in bit order
+        const int ones = min(x == (0xffffffffu >> b) ? 32 - b : __ffs((int)~x) - 1, nseg - s);
+        s += ones;
+        if (ones < 32 - b) break;
+    }
+    return s > e ? min(kSeg * (s - e), (int)tn - kSeg * e) : 0;
+}
+
+__device__ __forceinline__ LanePlan lane_plan(const unsigned* tile_runs, int warp, int lane, int nseg, unsigned tn, int len,
+                                              const unsigned long long* run_tab) {
     LanePlan p;
-    p.start = false; p.run = false; p.bytes = 0; p.next_bytes = 0; p.hbits = 0; p.size = 0;
-    if (lane >= nact) return p;
-    const unsigned act = nact == 32 ? FULL : ((1u << nact) - 1u);
-    const unsigned runm = run_mask & act;
-    const unsigned starts = ((runm ^ (runm << 1)) | 1u) & act;
-    p.run = (runm >> lane) & 1u;
-    p.start = (starts >> lane) & 1u;
-    if (!p.start) return p;
-    const unsigned after = lane == 31 ? 0u : (starts >> (lane + 1));
-    const int nl = after ? __ffs((int)after) : nact - lane;
-    p.bytes = min(kSeg * nl, wbytes - kSeg * lane);
-    BitWriter none;
+    p.start = false; p.run = false; p.hdr = false; p.bytes = 0; p.next_bytes = 0; p.hbits = 0; p.size = 0;
+    const int seg = warp * 32 + lane;
+    if (seg >= nseg) return p;
+    const unsigned my = tile_runs[warp];
+    p.run = (my >> lane) & 1u;
     if (p.run) {
-        const int m = lane + nl;
-        if (m < nact) {
-            const unsigned after2 = m == 31 ? 0u : (starts >> (m + 1));
-            const int nl2 = after2 ? __ffs((int)after2) : nact - m;
-            p.next_bytes = min(kSeg * nl2, wbytes - kSeg * m);
-        }
-        p.hbits = 3 + put_run<false>(none, p.bytes, d) + 7;
+        p.start = lane == 0 || !((my >> (lane - 1)) & 1u);
+        if (!p.start) return p;
+        const unsigned x = my >> lane;                                 // run segments from this lane on
+        const int nl = min(x == (0xffffffffu >> lane) ? 32 - lane : __ffs((int)~x) - 1, nseg - seg);
+        p.bytes = kSeg * nl;
+        p.next_bytes = literal_group_bytes(tile_runs, seg + nl, nseg, tn);
+        p.hbits = (int)(run_tab[nl - 1] >> 48);
         p.size = ((p.hbits + 3 + 7) >> 3) + 4;
     } else {
-        p.size = (lane == 0 ? 5 : 0) + p.bytes;
+        p.hdr = seg == 0;
+        p.start = p.hdr;
+        if (p.hdr) p.bytes = literal_group_bytes(tile_runs, 0, nseg, tn);
+        p.size = len + (p.hdr ? 5 : 0);
     }
     return p;
 }
 
-// emission: ybase = the warp's first byte in the staging area, off = this lane's exclusive prefix of the sizes
-__device__ __forceinline__ void lane_emit(const LanePlan& p, const SegMasks& m, unsigned run_mask, int nact, int d, uint8_t* Ys,
-                                          unsigned ybase, int off, int lane) {
+// whole bytes (at most 12) at byte offset `at` of the zeroed staging area
+__device__ __forceinline__ void stage_bytes(uint32_t* Y32, unsigned at, unsigned long long lo, uint32_t hi) {
+    const unsigned sh = 8u * (at & 3u), w0 = at >> 2;
+    uint32_t v0 = (uint32_t)lo, v1 = (uint32_t)(lo >> 32), v2 = hi, v3 = 0;
+    if (sh) { v3 = v2 >> (32u - sh); v2 = (v2 << sh) | (v1 >> (32u - sh)); v1 = (v1 << sh) | (v0 >> (32u - sh)); v0 <<= sh; }
+    if (v0) atomicOr(&Y32[w0], v0);
+    if (v1) atomicOr(&Y32[w0 + 1], v1);
+    if (v2) atomicOr(&Y32[w0 + 2], v2);
+    if (v3) atomicOr(&Y32[w0 + 3], v3);
+}
+
+// emission: at = this lane's place in the staging area (the tile's first byte + the exclusive prefix of the sizes)
+__device__ __forceinline__ void lane_emit(const LanePlan& p, const SegMasks& m, const unsigned long long* run_tab, uint8_t* Ys, unsigned at) {
     uint32_t* Y32 = reinterpret_cast<uint32_t*>(Ys);
     if (p.start) {
-        BitWriter bw;
-        bw.init(Y32, 8u * (ybase + (unsigned)off));
         if (p.run) {
-            bw.put(2u, 3);                                         // BFINAL 0, BTYPE 01
-            put_run<true>(bw, p.bytes, d);
-            bw.put(0u, 7);                                         // end of block
-            bw.put(0u, 3 + ((-(p.hbits + 3)) & 7));                // stored header, padding to the byte boundary
-            bw.put((uint32_t)p.next_bytes | ((~(uint32_t)p.next_bytes & 0xffffu) << 16), 32);
-        } else if (lane == 0) {
-            bw.put(0u, 8);
-            bw.put((uint32_t)p.bytes | ((~(uint32_t)p.bytes & 0xffffu) << 16), 32);
+            // the fixed block, the header of the stored block behind it (three zero bits + padding), LEN / NLEN
+            const unsigned long long blk = run_tab[p.bytes / kSeg - 1] & 0xffffffffffffull;
+            const int nb1 = (p.hbits + 3 + 7) >> 3;                // <= 7 bytes
+            const uint32_t len = (uint32_t)p.next_bytes | ((~(uint32_t)p.next_bytes & 0xffffu) << 16);
+            unsigned long long lo = blk;
+            uint32_t hi = 0;
+            lo |= (unsigned long long)len << (8 * nb1);
+            if (nb1 > 4) hi = len >> (8 * (8 - nb1));
+            stage_bytes(Y32, at, lo, hi);
+        } else {
+            const uint32_t len = (uint32_t)p.bytes | ((~(uint32_t)p.bytes & 0xffffu) << 16);
+            stage_bytes(Y32, at, (unsigned long long)len << 8, 0u);
         }
-        bw.finish();
     }
-    // literal lanes: the start lane of my block, its offset, my 16 bytes behind it
-    const unsigned act = nact == 32 ? FULL : ((1u << nact) - 1u);
-    const unsigned runm = run_mask & act;
-    const unsigned starts = ((runm ^ (runm << 1)) | 1u) & act;
-    const unsigned below = starts & (lane == 31 ? FULL : ((2u << lane) - 1u));
-    const int ms = below ? 31 - __clz((int)below) : 0;
-    const int off_ms = __shfl_sync(FULL, off, ms);
-    if (lane < nact && !p.run && m.len > 0) {
-        const unsigned a = ybase + (unsigned)off_ms + (ms == 0 ? 5u : 0u) + (unsigned)(kSeg * (lane - ms));
+    if (!p.run && m.len > 0) {
+        const unsigned a = at + (p.hdr ? 5u : 0u);
         const unsigned r = a & 3u, w0 = a >> 2;
         if (r == 0) {
 #pragma unroll
@@ -284,15 +275,119 @@ __device__ __forceinline__ void lane_emit(const LanePlan& p, const SegMasks& m, 
     }
 }
 
+// CRC-32 tables for slicing by four, built by 256 threads: T[k][b] = register after byte b and k zero bytes
+__device__ __forceinline__ void crc_tables(uint32_t (*T)[256], int tid) {
+    uint32_t c = (uint32_t)tid;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c = (c & 1) ? (c >> 1) ^ kCrcPoly : c >> 1;
+        T[k][tid] = c;
+    }
+}
+__device__ __forceinline__ uint32_t crc_word(const uint32_t (*T)[256], uint32_t c, uint32_t w) {
+    c ^= w;
+    return T[3][c & 0xffu] ^ T[2][(c >> 8) & 0xffu] ^ T[1][(c >> 16) & 0xffu] ^ T[0][c >> 24];
+}
+__device__ __forceinline__ uint32_t crc_byte(const uint32_t (*T)[256], uint32_t c, uint32_t b) { return T[0][(c ^ b) & 0xffu] ^ (c >> 8); }
+
+// the 16 raw bytes of segment `tid` of the tile at `tb` (zeros behind the end of the stream).  Image mode inserts the filter
+// byte 0 in front of every scanline; plain mode reads prefix + body, the body optionally expanded from uint8 to float32.
+__device__ __forceinline__ uint4 load_seg(const ZArgs& a, const uint8_t* __restrict__ src, const uint8_t* __restrict__ pfx, unsigned plen,
+                                          bool image, unsigned rl, unsigned rl_magic, unsigned long long r0, unsigned tb, unsigned n, int tid) {
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    const unsigned b = tb + (unsigned)(kSeg * tid);
+    if (b < n && !a.zero_source) {
+        const unsigned cnt = min((unsigned)kSeg, n - b);
+        if (image) {
+            const unsigned r = __umulhi(b, rl_magic), c0 = b - r * rl;
+            const uint8_t* p = src + (size_t)r * (rl - 1) + (c0 ? c0 - 1 : 0);    // the next data byte
+            if (rl > (unsigned)kSeg) {
+                // at most one filter byte in the segment, at j: 16 data bytes from aligned words, then a zero byte shifted in
+                const unsigned j = c0 == 0 ? 0u : rl - c0;
+                const unsigned ndata = cnt - (j < cnt ? 1u : 0u);
+                const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3);
+                const uint32_t* a32 = reinterpret_cast<const uint32_t*>(p - mis);
+                uint32_t q[kSeg / 4 + 1];
+#pragma unroll
+                for (int k = 0; k <= kSeg / 4; ++k) q[k] = (unsigned)(4 * k) < mis + ndata ? __ldg(a32 + k) : 0u;     // only words that hold a data byte
+                uint32_t D[kSeg / 4];
+#pragma unroll
+                for (int k = 0; k < kSeg / 4; ++k) D[k] = __funnelshift_r(q[k], q[k + 1], 8 * mis);
+                const unsigned jw = j >> 2, jb = j & 3u;
+                const uint32_t below = (1u << (8 * jb)) - 1u, upto = 0xffffffffu >> (8 * (3 - jb));
+#pragma unroll
+                for (int k = 0; k < kSeg / 4; ++k) {
+                    const uint32_t S = k ? __funnelshift_l(D[k - 1], D[k], 8) : D[0] << 8;
+                    w[k] = (unsigned)k < jw ? D[k] : ((unsigned)k > jw ? S : ((D[k] & below) | (S & ~upto)));
+                }
+                if (cnt < (unsigned)kSeg) {
+#pragma unroll
+                    for (int k = 0; k < kSeg / 4; ++k) {
+                        const int left = (int)cnt - 4 * k;
+                        if (left <= 0) w[k] = 0; else if (left < 4) w[k] &= (1u << (8 * left)) - 1u;
+                    }
+                }
+            } else {
+                unsigned c = c0;
+#pragma unroll
+                for (int k = 0; k < kSeg; ++k) {
+                    const bool data = c != 0;
+                    uint32_t v = 0;
+                    if ((unsigned)k < cnt && data) v = __ldg(p);
+                    p += data ? 1 : 0;
+                    c = c + 1 == rl ? 0u : c + 1;
+                    w[k >> 2] |= v << (8 * (k & 3));
+                }
+            }
+        } else {
+            const unsigned long long g = r0 + b;
+            if (!a.expand && g >= plen && cnt == kSeg && (reinterpret_cast<uintptr_t>(src + (g - plen)) & 15) == 0) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (g - plen)));
+                return v;
+            } else if (a.expand && g >= plen && ((g - plen) & 3) == 0 && (cnt & 3) == 0) {
+                // uint8 mask stored as float32: one mask byte per output word (0.0f / 1.0f)
+                const uint8_t* body = src + ((g - plen) >> 2);
+                uint32_t mk = 0;
+                if (cnt == kSeg && (reinterpret_cast<uintptr_t>(body) & 3) == 0) mk = __ldg(reinterpret_cast<const uint32_t*>(body));
+                else {
+#pragma unroll
+                    for (int k = 0; k < kSeg / 4; ++k) if ((unsigned)(4 * k) < cnt) mk |= (uint32_t)__ldg(body + k) << (8 * k);
+                }
+#pragma unroll
+                for (int k = 0; k < kSeg / 4; ++k) w[k] = ((mk >> (8 * k)) & 0xffu) ? 0x3f800000u : 0u;
+            } else {
+#pragma unroll
+                for (int k = 0; k < kSeg; ++k) if ((unsigned)k < cnt) {
+                    const unsigned long long gg = g + k;
+                    uint32_t v;
+                    if (gg < plen) v = __ldg(pfx + gg);
+                    else if (!a.expand) v = __ldg(src + (gg - plen));
+                    else {
+                        const unsigned long long bb = gg - plen;
+                        v = __ldg(src + (bb >> 2)) ? (0x3f800000u >> (8 * (unsigned)(bb & 3))) & 0xffu : 0u;
+                    }
+                    w[k >> 2] |= v << (8 * (k & 3));
+                }
+            }
+        }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+
 __global__ void __launch_bounds__(kZThreads, 4) deflate_kernel(const ZArgs a) {
     __shared__ __align__(16) uint8_t Xs[kLook + kTile + 4 * (kZThreads + 2) + 16];
-    __shared__ __align__(16) uint8_t Ys[kYBytes + 16];
-    __shared__ uint32_t crc_table[256];
-    __shared__ uint32_t crc_part[kZThreads];
+    __shared__ __align__(16) uint8_t Ys2[2][kYBytes + 16];
+    __shared__ uint32_t crc_table[4][256];            // slicing by four: table k = a byte followed by k zero bytes
+    __shared__ uint32_t crc_part[kZThreads / 32];
+    __shared__ unsigned long long run_tab[32];
+    __shared__ unsigned tile_runs[kZThreads / 32];     // bit l of word w: segment 32 w + l of the tile lies inside a run
     __shared__ int scan_w[kZThreads / 32];
     __shared__ unsigned long long red_a[kZThreads / 32], red_b[kZThreads / 32];
-    __shared__ unsigned s_state[4];     // [0] bits carried in Ys, [1] bytes written to the slot, [2] running CRC
+    __shared__ unsigned s_state[4];     // [3] bytes of the last flush
     uint8_t* X = Xs + kLook;
+    uint8_t* Ys = Ys2[0];
     uint32_t* Y32 = reinterpret_cast<uint32_t*>(Ys);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned s = blockIdx.x;
@@ -316,12 +411,8 @@ __global__ void __launch_bounds__(kZThreads, 4) deflate_kernel(const ZArgs a) {
     const unsigned rl_magic = image ? (unsigned)(0x100000000ull / rl) + 1u : 0u;   // g / rl == umulhi(g, magic) for g * rl < 2^32
 
     const int dist = a.dist2 ? a.dist2 : 1;
-    if (want_crc) {
-        uint32_t c = (uint32_t)tid;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ kCrcPoly : c >> 1;
-        crc_table[tid] = c;
-    }
+    if (want_crc) crc_tables(crc_table, tid);
+    if (tid < 32) run_tab[tid] = run_block(tid, dist);
     for (int q0_ = 0; q0_ < ((kYBytes + 16) / 4); q0_ += kZThreads) if (const int q = q0_ + (int)tid; q < ((kYBytes + 16) / 4)) Y32[q] = 0;
     if (tid < kLook / 4) reinterpret_cast<uint32_t*>(Xs)[tid] = 0;
     block_sync();
@@ -345,115 +436,107 @@ __global__ void __launch_bounds__(kZThreads, 4) deflate_kernel(const ZArgs a) {
             Ys[37] = 'I'; Ys[38] = 'D'; Ys[39] = 'A'; Ys[40] = 'T';       // [33, 37): IDAT length, patched by pack_kernel
             Ys[41] = 0x78; Ys[42] = 0x01;
         }
-        s_state[0] = 8 * hdr; s_state[1] = 0; s_state[2] = 0;          // [0]: bits carried in the staging area (whole bytes)
+    }
+    // bits carried in the staging area and bytes already in the slot: every thread keeps its own copy
+    unsigned bit0 = 8 * hdr, done = 0;
+    uint32_t crc_run = 0;                               // thread 0: running CRC-32 (zero-register form) and all-zero tiles not yet applied
+    int crc_pend = 0;
+    uint4 P = load_seg(a, src, pfx, plen, image, rl, rl_magic, r0, 0u, n, tid);
+    if (a.tmpl && !image && n == a.chunk && n <= 4u * kTile && r0 >= plen) {
+        // A full chunk without header bytes: when every byte of it is zero (two thirds of a skull-stripped volume, nearly all of a
+        // mask) its stream is the same for every such chunk - built once per launch, copied here
+        uint32_t nz = P.x | P.y | P.z | P.w;
+        for (unsigned tb = kTile; tb < n; tb += kTile) {
+            const uint4 q = load_seg(a, src, pfx, plen, image, rl, rl_magic, r0, tb, n, tid);
+            nz |= q.x | q.y | q.z | q.w;
+        }
+        __syncwarp();
+        if (!__syncthreads_or(nz != 0)) {
+            const uint32_t* tm = reinterpret_cast<const uint32_t*>(a.tmpl);
+            const unsigned fsize = tm[0];
+            const uint4* t4 = reinterpret_cast<const uint4*>(a.tmpl + 16);
+            uint4* d4 = reinterpret_cast<uint4*>(slot);
+            for (unsigned q0_ = 0; q0_ < ((fsize + 15) >> 4); q0_ += kZThreads) if (const unsigned q = q0_ + (unsigned)tid; q < ((fsize + 15) >> 4)) d4[q] = t4[q];
+            if (tid < 4) a.meta[4 * (size_t)s + tid] = tm[tid];
+            return;
+        }
     }
     block_sync();
 
     unsigned long long sa = 0, sb = 0;                  // Adler-32 partial sums
+    int cur = 0;
     for (unsigned tb = 0; tb < n || tb == 0; tb += kTile) {
         const unsigned tn = min((unsigned)kTile, n - tb);
-        // ---- load the tile (image mode inserts the filter byte 0 in front of every scanline)
-        if (!image) {
-            const unsigned long long g0 = r0 + tb;            // raw offset of the tile inside the source
-            if (!a.expand && g0 >= plen && (reinterpret_cast<uintptr_t>(src + (g0 - plen)) & 15) == 0) {
-                const uint8_t* body = src + (g0 - plen);
-                const uint4* s4 = reinterpret_cast<const uint4*>(body);
-                for (unsigned q0_ = 0; q0_ < ((tn >> 4)); q0_ += kZThreads) if (const unsigned q = q0_ + (unsigned)tid; q < ((tn >> 4))) {
-                    const uint4 v = __ldg(s4 + q);
-                    uint32_t* x32 = reinterpret_cast<uint32_t*>(X + xphys((int)(16 * q)));      // 4-byte aligned (16-byte groups stay inside a segment)
-                    x32[0] = v.x; x32[1] = v.y; x32[2] = v.z; x32[3] = v.w;
-                }
-                if (const unsigned i = (tn & ~15u) + tid; i < tn) XP((int)i) = __ldg(body + i);       // (< 16 bytes)
-            } else if (a.expand && g0 >= plen && ((g0 - plen) & 3) == 0) {
-                // uint8 mask stored as float32: one mask byte per output word (0.0f / 1.0f)
-                const uint8_t* body = src + ((g0 - plen) >> 2);
-                for (unsigned q0_ = 0; q0_ < ((tn + 3) >> 2); q0_ += kZThreads) if (const unsigned q = q0_ + (unsigned)tid; q < ((tn + 3) >> 2))
-                    *reinterpret_cast<uint32_t*>(X + xphys((int)(4 * q))) = __ldg(body + q) ? 0x3f800000u : 0u;
-            } else {
-                for (unsigned i0_ = 0; i0_ < (tn); i0_ += kZThreads) if (const unsigned i = i0_ + (unsigned)tid; i < (tn)) {
-                    const unsigned long long g = g0 + i;
-                    uint8_t v;
-                    if (g < plen) v = __ldg(pfx + g);
-                    else if (!a.expand) v = __ldg(src + (g - plen));
-                    else {
-                        const unsigned long long b = g - plen;
-                        const uint8_t m = __ldg(src + (b >> 2));
-                        v = m ? (uint8_t)(0x3f800000u >> (8 * (unsigned)(b & 3))) : (uint8_t)0;
-                    }
-                    XP((int)i) = v;
-                }
-            }
-        } else {
-            // all of the thread's loads are issued before the first one is used
-            uint8_t v[kTile / kZThreads];
-#pragma unroll
-            for (int j = 0; j < kTile / kZThreads; ++j) {
-                const unsigned i = tid + j * kZThreads;
-                v[j] = 0;
-                if (i < tn) {
-                    const unsigned g = tb + i, r = __umulhi(g, rl_magic), c = g - r * rl;
-                    if (c) v[j] = __ldg(src + (size_t)r * (rl - 1) + (c - 1));
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < kTile / kZThreads; ++j) {
-                const unsigned i = tid + j * kZThreads;
-                if (i < tn) XP((int)i) = v[j];
-            }
+        Ys = Ys2[cur];
+        Y32 = reinterpret_cast<uint32_t*>(Ys);
+        // ---- the tile into shared memory (loaded one iteration ahead); the other staging buffer is cleared meanwhile
+        {
+            uint32_t* x32 = reinterpret_cast<uint32_t*>(X + xphys(tid * kSeg));
+            x32[0] = P.x; x32[1] = P.y; x32[2] = P.z; x32[3] = P.w;
         }
         block_sync();
+        const bool last = tb + kTile >= n;
+        if (!last) P = load_seg(a, src, pfx, plen, image, rl, rl_magic, r0, tb + kTile, n, tid);
+        {
+            uint4* o4 = reinterpret_cast<uint4*>(Ys2[cur ^ 1]);
+            for (int q0_ = 0; q0_ < (kYBytes + 16) / 16; q0_ += kZThreads) if (const int q = q0_ + tid; q < (kYBytes + 16) / 16) o4[q] = make_uint4(0, 0, 0, 0);
+        }
         // ---- the thread's segment as masks; checksums of the raw bytes
         const int beg = tid * kSeg, end = min(beg + kSeg, (int)tn);
         const SegMasks m = seg_masks(X, beg, end, (long long)tb, dist);
         if (want_adler) { sa += m.s1; sb += (unsigned long long)(n - (tb + beg)) * m.s1 - m.s2; }
-        if (want_crc && tn > 0) {
-            if (__syncwarp(), !__syncthreads_or(m.any != 0 || tb < 4u)) {
-                // an all-zero tile: a zero-initialised CRC register stays zero, only the running value moves on
-                if (tid == 0) s_state[2] = gf_mul(s_state[2], tn == kTile ? a.crc_tile : (tn == a.crc_part_len[0] ? a.crc_part_mul[0] : (tn == a.crc_part_len[1] ? a.crc_part_mul[1] : gf_xpow8(tn))));
+        const bool isrun = m.len == kSeg && m.E == ((1ull << kSeg) - 1ull);
+        const unsigned run_mask = __ballot_sync(FULL, isrun);
+        if (lane == 0) tile_runs[warp] = run_mask;
+        bool crc_fold = false;
+        if (!(want_crc && tn > 0)) block_sync();
+        else {
+            if (__syncwarp(), !__syncthreads_or(m.any != 0 || tb < 4u || tn != (unsigned)kTile)) {
+                // an all-zero tile: a zero-initialised CRC register stays zero, only the running value moves on - lazily, by
+                // up to four tiles at once
+                if (tid == 0 && ++crc_pend == 4) { crc_run = gf_mul(crc_run, a.crc_tilek[3]); crc_pend = 0; }
             } else {
-                // right-aligned segments: thread t takes the 16 bytes that end (255 - t) segments before the end of the tile, so
-                // that short tiles leave the FRONT threads short (a zero register is unchanged by missing leading bytes).  The
-                // all-ones initial register of CRC-32 is folded in by complementing the first four bytes of the stream.
-                const int e = (int)tn - (kZThreads - 1 - tid) * kSeg, b = e - kSeg;
+                // the thread's own 16 bytes (the all-ones initial register of CRC-32 is folded in by complementing the first
+                // four bytes of the stream; thread 0 starts from the running value instead of zero), moved to the end of the
+                // tile by ONE multiplication with x^(8 * bytes behind the segment); the XOR of the 256 values is the new
+                // running value (partials travel with the block scan's barrier)
                 uint32_t c = 0;
-                for (int i = max(b, 0); i < e; ++i) {
-                    uint32_t v = XP(i);
-                    if (tb + (unsigned)i < 4u) v ^= 0xffu;
-                    c = crc_table[(c ^ v) & 0xffu] ^ (c >> 8);
+                if (tid == 0) {
+                    if (crc_pend) { crc_run = gf_mul(crc_run, a.crc_tilek[crc_pend - 1]); crc_pend = 0; }
+                    c = crc_run;
                 }
-                // every partial is moved to the end of the tile by ONE multiplication, then the 256 values are XOR-ed
-                c = e > 0 ? gf_mul(a.crcP[kZThreads - 1 - tid], c) : 0u;
+#pragma unroll
+                for (int k = 0; k < kSeg / 4; ++k) if (4 * k + 4 <= m.len) c = crc_word(crc_table, c, (tb == 0 && tid == 0 && k == 0) ? ~m.w[0] : m.w[k]);
+                for (int i = m.len & ~3; i < m.len; ++i) c = crc_byte(crc_table, c, XP(beg + i));   // (streams of fewer than four bytes are redone below)
+                if (m.len == kSeg) {
+                    const int full = (int)(tn >> 4), rem = (int)(tn & 15u);        // bytes behind me: 16 * (full - 1 - tid) + rem
+                    for (int i = 0; i < rem; ++i) c = crc_byte(crc_table, c, 0u);
+                    c = gf_mul(a.crcP[full - 1 - tid], c);
+                }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) c ^= __shfl_xor_sync(FULL, c, o);
                 if (lane == 0) crc_part[warp] = c;
-                block_sync();
-                if (tid == 0) {
-                    uint32_t t = 0;
-                    for (int w = 0; w < kZThreads / 32; ++w) t ^= crc_part[w];
-                    const uint32_t mul = tn == kTile ? a.crc_tile : (tn == a.crc_part_len[0] ? a.crc_part_mul[0] : (tn == a.crc_part_len[1] ? a.crc_part_mul[1] : gf_xpow8(tn)));
-                    s_state[2] = gf_mul(s_state[2], mul) ^ t;
-                }
+                crc_fold = true;
             }
         }
-        // ---- blocks per warp: sizes from the ballot, a block scan over the warps, emission
-        const bool isrun = m.len == kSeg && m.E == ((1ull << kSeg) - 1ull);
-        const unsigned run_mask = __ballot_sync(FULL, isrun);
-        const int wbeg = warp * 32 * kSeg;
-        const int wbytes = max(0, min(32 * kSeg, (int)tn - wbeg));
-        const int nact = (wbytes + kSeg - 1) / kSeg;
-        const LanePlan plan = lane_plan(run_mask, nact, wbytes, dist, lane);
+        // ---- blocks: sizes from the run masks of the tile, a scan over lanes and warps, emission
+        const LanePlan plan = lane_plan(tile_runs, warp, lane, (int)((tn + kSeg - 1) / kSeg), tn, m.len, run_tab);
         const int lincl = warp_incl_scan(plan.size, lane);
         if (lane == 31) scan_w[warp] = lincl;
         block_sync();
         int wbase = 0, total = 0;
 #pragma unroll
         for (int w = 0; w < kZThreads / 32; ++w) { const int v = scan_w[w]; if (w < warp) wbase += v; total += v; }
-        const unsigned bit0 = s_state[0];
-        lane_emit(plan, m, run_mask, nact, dist, Ys, (bit0 >> 3) + (unsigned)wbase, lincl - plan.size, lane);
+        if (crc_fold && tid == 0) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int w = 0; w < kZThreads / 32; ++w) t ^= crc_part[w];
+            crc_run = t;
+        }
+        lane_emit(plan, m, run_tab, Ys, (bit0 >> 3) + (unsigned)(wbase + lincl - plan.size));
         total *= 8;
         block_sync();
-        unsigned nbits = bit0 + (unsigned)total;
-        const bool last = tb + kTile >= n;
+        const unsigned nbits = bit0 + (unsigned)total;
         if (last) {
             // end of block (symbol 256: seven zero bits), byte alignment, trailer
             if (want_adler) {
@@ -473,10 +556,11 @@ __global__ void __launch_bounds__(kZThreads, 4) deflate_kernel(const ZArgs a) {
                     Ys[nb] = chk >> 24; Ys[nb + 1] = chk >> 16; Ys[nb + 2] = chk >> 8; Ys[nb + 3] = chk;
                     nb += 4;
                 } else if (want_crc) {
-                    if (n >= 4) chk = s_state[2] ^ 0xffffffffu;
+                    if (crc_pend) crc_run = gf_mul(crc_run, a.crc_tilek[crc_pend - 1]);
+                    if (n >= 4) chk = crc_run ^ 0xffffffffu;
                     else {                                  // streams shorter than the register: the plain definition (the tile is still in X)
                         uint32_t c = 0xffffffffu;
-                        for (unsigned i = 0; i < n; ++i) c = crc_table[(c ^ XP((int)i)) & 0xffu] ^ (c >> 8);
+                        for (unsigned i = 0; i < n; ++i) c = crc_byte(crc_table, c, XP((int)i));
                         chk = ~c;
                     }
                     Ys[nb] = chk; Ys[nb + 1] = chk >> 8; Ys[nb + 2] = chk >> 16; Ys[nb + 3] = chk >> 24;
@@ -491,72 +575,63 @@ __global__ void __launch_bounds__(kZThreads, 4) deflate_kernel(const ZArgs a) {
                     nb += 16;
                     idat_type = 37;
                 }
-                const unsigned fsize = s_state[1] + nb;
+                const unsigned fsize = done + nb;
                 uint32_t* m = a.meta + 4 * (size_t)s;
                 m[0] = fsize; m[1] = n; m[2] = chk; m[3] = idat_type;
                 if (a.container == MSL_Z_GZIP) {
                     // compressed member size and raw size into the 'MS' extra subfield (bytes 16..23 of the member): still in
                     // the staging area for a one-tile stream, already in the slot (flushed before earlier barriers) otherwise
-                    uint8_t* h = s_state[1] == 0 ? Ys + 16 : slot + 16;
+                    uint8_t* h = done == 0 ? Ys + 16 : slot + 16;
                     h[0] = fsize; h[1] = fsize >> 8; h[2] = fsize >> 16; h[3] = fsize >> 24;
                     h[4] = n; h[5] = n >> 8; h[6] = n >> 16; h[7] = n >> 24;
                 }
                 s_state[3] = nb;
             }
             block_sync();
-            const unsigned nb = s_state[3], done = s_state[1];
+            const unsigned nb = s_state[3];
             uint4* d4 = reinterpret_cast<uint4*>(slot + done);
             const uint4* y4 = reinterpret_cast<const uint4*>(Ys);
             for (unsigned q0_ = 0; q0_ < (((nb + 15) >> 4)); q0_ += kZThreads) if (const unsigned q = q0_ + (unsigned)tid; q < (((nb + 15) >> 4))) d4[q] = y4[q];
             break;
         }
-        // ---- flush whole 16-byte groups, carry the rest to the front of the staging area
-        const unsigned nfl = (nbits >> 3) & ~15u, done = s_state[1];
+        // ---- flush whole 16-byte groups, carry the rest to the front of the other staging buffer
+        const unsigned nfl = (nbits >> 3) & ~15u;
         {
             uint4* d4 = reinterpret_cast<uint4*>(slot + done);
             const uint4* y4 = reinterpret_cast<const uint4*>(Ys);
             for (unsigned q0_ = 0; q0_ < ((nfl >> 4)); q0_ += kZThreads) if (const unsigned q = q0_ + (unsigned)tid; q < ((nfl >> 4))) d4[q] = y4[q];
         }
-        uint4 carry = make_uint4(0, 0, 0, 0);
-        if (tid == 0) carry = *reinterpret_cast<const uint4*>(Ys + nfl);          // < 16 bytes and a partial byte remain
-        if (tid == 1) carry = *reinterpret_cast<const uint4*>(Ys + nfl + 16);
-        block_sync();
-        for (int q0_ = 0; q0_ < ((kYBytes + 16) / 4); q0_ += kZThreads) if (const int q = q0_ + (int)tid; q < ((kYBytes + 16) / 4)) Y32[q] = 0;
-        // the look-back of the next tile = the tail of this one
-        uint32_t lb = 0;
-        if (tid < kLook / 4) lb = *reinterpret_cast<const uint32_t*>(X + xphys(kTile - kLook + 4 * tid));
-        block_sync();
-        if (tid == 0) { *reinterpret_cast<uint4*>(Ys) = carry; s_state[0] = nbits - 8 * nfl; s_state[1] = done + nfl; }
-        if (tid == 1) *reinterpret_cast<uint4*>(Ys + 16) = carry;
-        if (tid < kLook / 4) reinterpret_cast<uint32_t*>(Xs)[tid] = lb;
-        block_sync();
+        if (tid < 2) *reinterpret_cast<uint4*>(Ys2[cur ^ 1] + 16 * tid) = *reinterpret_cast<const uint4*>(Ys + nfl + 16 * tid);   // < 16 bytes and a partial byte remain
+        // the look-back of the next tile = the last segment of this one (still in its owner's registers)
+        if (tid == kZThreads - 1) *reinterpret_cast<uint4*>(Xs) = make_uint4(m.w[0], m.w[1], m.w[2], m.w[3]);
+        bit0 = nbits - 8 * nfl;
+        done += nfl;
+        cur ^= 1;
     }
 }
 
-// exclusive scan of the stream sizes -> byte offsets of the packed streams (one CTA; n is a few ten thousand at most)
+// exclusive scan of the stream sizes -> byte offsets of the packed streams.  One CTA: every thread sums a run of consecutive
+// sizes, one block scan of the 1024 partial sums, then the run is written out (n is a few ten thousand at most).
 __global__ void __launch_bounds__(1024) scan_sizes_kernel(const uint32_t* meta, int n, unsigned align, unsigned long long* off) {
     __shared__ unsigned long long wsum[32];
-    __shared__ unsigned long long carry_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry_s = 0;
-    block_sync();
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + tid;
-        unsigned long long v = i < n ? (((unsigned long long)meta[4 * (size_t)i] + align - 1) / align) * align : 0ull;
-        unsigned long long inc = v;
+    const int per = (n + 1023) / 1024;
+    const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
+    unsigned long long v = 0;
+    for (int i = i0; i < i1; ++i) v += (((unsigned long long)meta[4 * (size_t)i] + align - 1) / align) * align;
+    unsigned long long inc = v;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
-        if (lane == 31) wsum[warp] = inc;
-        block_sync();
-        unsigned long long wb = 0, tot = 0;
-        for (int w = 0; w < 32; ++w) { if (w < warp) wb += wsum[w]; tot += wsum[w]; }
-        const unsigned long long c = carry_s;
-        if (i < n) off[i] = c + wb + inc - v;
-        block_sync();
-        if (tid == 0) carry_s = c + tot;
-        block_sync();
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[warp] = inc;
+    block_sync();
+    unsigned long long wb = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) { const unsigned long long t = wsum[w]; if (w < warp) wb += t; tot += t; }
+    unsigned long long run = wb + inc - v;
+    for (int i = i0; i < i1; ++i) {
+        off[i] = run;
+        run += (((unsigned long long)meta[4 * (size_t)i] + align - 1) / align) * align;
     }
-    if (tid == 0) off[n] = carry_s;
+    if (tid == 0) off[n] = tot;
 }
 
 // copies stream s from its slot to out + off[s]; PNG: IDAT length and CRC-32 over (type + compressed data)
@@ -572,7 +647,7 @@ struct PackArgs {
 };
 
 __global__ void __launch_bounds__(kZThreads) pack_kernel(const PackArgs a) {
-    __shared__ uint32_t crc_table[256];
+    __shared__ uint32_t crc_table[4][256];
     __shared__ uint32_t part[kZThreads / 32];
     __shared__ uint32_t s_run;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -585,48 +660,69 @@ __global__ void __launch_bounds__(kZThreads) pack_kernel(const PackArgs a) {
     uint32_t clen = 0;                                      // PNG: bytes the IDAT CRC covers = "IDAT" + zlib stream
     if (idat) {
         clen = fsize - idat - 16;                           // file = ... [idat - 4: length][idat: "IDAT" + data][CRC][IEND chunk: 12]
-        uint32_t c = (uint32_t)tid;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ kCrcPoly : c >> 1;
-        crc_table[tid] = c;
+        crc_tables(crc_table, tid);
         if (tid == 0) s_run = 0;
     }
-    // aligned body: destination words, source read byte-wise when the packed offset is not aligned
+    // destination words; the source (16-byte aligned slots) is read as aligned words and shifted into place
     const unsigned head = (unsigned)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);
     const unsigned h = min(head, fsize);
     if (tid < (int)h) dst[tid] = slot[tid];
     const unsigned nwords = (fsize - h) >> 2;
-    if (((reinterpret_cast<uintptr_t>(slot) + h) & 3) == 0) {
-        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(slot + h);
+    {
+        const unsigned ms = (unsigned)((reinterpret_cast<uintptr_t>(slot) + h) & 3);
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(slot + h - ms);
         uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + h);
-        for (unsigned q0_ = 0; q0_ < (nwords); q0_ += kZThreads) if (const unsigned q = q0_ + (unsigned)tid; q < (nwords)) d32[q] = s32[q];
-    } else {
-        uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + h);
-        for (unsigned q0_ = 0; q0_ < (nwords); q0_ += kZThreads) if (const unsigned q = q0_ + (unsigned)tid; q < (nwords)) {
-            const uint8_t* p = slot + h + 4 * q;
-            d32[q] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+        if (ms == 0) {
+            for (unsigned q0_ = 0; q0_ < nwords; q0_ += kZThreads) if (const unsigned q = q0_ + (unsigned)tid; q < nwords) d32[q] = s32[q];
+        } else {
+            for (unsigned q0_ = 0; q0_ < nwords; q0_ += kZThreads) if (const unsigned q = q0_ + (unsigned)tid; q < nwords)
+                d32[q] = __funnelshift_r(s32[q], s32[q + 1], 8 * ms);      // (the slot has slack behind the stream)
         }
     }
     if (const unsigned i = h + 4 * nwords + tid; i < fsize) dst[i] = slot[i];                       // (< 4 bytes)
     if (!idat) return;
     block_sync();
     // CRC-32 of the IDAT chunk in tiles of 16 KB that are aligned to the END of the chunk (only the first tile is short, and a
-    // zero register does not see missing leading bytes): a thread takes 64 bytes, moves its value to the end of the tile with
-    // one multiplication, the tile's XOR is folded into the running value.  The all-ones initial register = the first four
-    // bytes complemented.
+    // zero register does not see missing leading bytes): a thread takes 64 bytes (aligned words shifted into place, four
+    // bytes per table step), moves its value to the end of the tile with one multiplication, the tile's XOR is folded into
+    // the running value.  The all-ones initial register = the first four bytes complemented.
     const uint8_t* C = slot + idat;
     const int ntile = (int)((clen + 16383u) >> 14);
     for (int j = 0; j < ntile; ++j) {
         const long long te = (long long)clen - (long long)(ntile - 1 - j) * 16384;
         const long long e = te - (long long)(kZThreads - 1 - tid) * 64, b = e - 64;
-        uint32_t c = 0;
         const long long lo = max(b, max(te - 16384, 0ll));
-        for (long long i = lo; i < e; ++i) {
-            uint32_t v = C[i];
-            if (i < 4) v ^= 0xffu;
-            c = crc_table[(c ^ v) & 0xffu] ^ (c >> 8);
+        const int count = e > lo ? (int)(e - lo) : 0;
+        uint32_t c = 0;
+        if (count > 0) {
+            const uint8_t* p = C + lo;
+            const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3);
+            const uint32_t* a32 = reinterpret_cast<const uint32_t*>(p - mis);
+            const uint32_t flip0 = lo >= 4 ? 0u : (lo == 0 ? 0xffffffffu : (1u << (8 * (4 - (int)lo))) - 1u);
+            if (count == 64) {
+                uint32_t q[17];
+#pragma unroll
+                for (int k = 0; k < 17; ++k) q[k] = (k < 16 || mis) ? a32[k] : 0u;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    uint32_t w = __funnelshift_r(q[k], q[k + 1], 8 * mis);
+                    if (k == 0) w ^= flip0;
+                    c = crc_word(crc_table, c, w);
+                }
+            } else {
+                const int nw = count >> 2;
+                uint32_t prev = a32[0];
+                for (int k = 0; k <= nw; ++k) {
+                    const uint32_t nxt = (unsigned)(4 * (k + 1)) < mis + (unsigned)count ? a32[k + 1] : 0u;
+                    uint32_t w = __funnelshift_r(prev, nxt, 8 * mis);
+                    if (k == 0) w ^= flip0;
+                    if (k < nw) c = crc_word(crc_table, c, w);
+                    else for (int t = 0; t < (count & 3); ++t) c = crc_byte(crc_table, c, (w >> (8 * t)) & 0xffu);
+                    prev = nxt;
+                }
+            }
+            c = gf_mul(a.P64[kZThreads - 1 - tid], c);
         }
-        c = e > lo ? gf_mul(a.P64[kZThreads - 1 - tid], c) : 0u;
 #pragma unroll
         for (int o2 = 16; o2 > 0; o2 >>= 1) c ^= __shfl_xor_sync(FULL, c, o2);
         if (lane == 0) part[warp] = c;
@@ -658,7 +754,8 @@ size_t deflate_slot_bytes(int container, size_t raw) {
 }
 
 size_t deflate_workspace_bytes(int n, int container, size_t raw) {
-    return (size_t)n * deflate_slot_bytes(container, raw) + (((size_t)n * 16 + 255) & ~(size_t)255);
+    // meta rows, the slots, and the template of an all-zero chunk (meta row + one slot)
+    return (size_t)(n + 1) * deflate_slot_bytes(container, raw) + (((size_t)n * 16 + 255) & ~(size_t)255) + 16;
 }
 
 int launch_deflate_pack(const uint8_t* src, int n, size_t src_pitch, size_t chunk, size_t total, int rows, int row_bytes,
@@ -686,22 +783,30 @@ int launch_deflate_pack(const uint8_t* src, int n, size_t src_pitch, size_t chun
     a.slot_pitch = deflate_slot_bytes(container, raw);
     {
         // x^(8 * kSeg * k), k = 0 .. 255, and the multipliers of the partial tiles whose length is known here
-        struct Tab { uint32_t P[kZThreads]; uint32_t tile; };
+        struct Tab { uint32_t P[kZThreads]; uint32_t tile[4]; };
         static const Tab tab = [] {
             Tab t;
             const uint32_t step = gf_xpow8(kSeg);
             uint32_t v = 1u << 31;
             for (int k = 0; k < kZThreads; ++k) { t.P[k] = v; v = gf_mul(v, step); }
-            t.tile = gf_xpow8(kTile);
+            for (int k = 0; k < 4; ++k) t.tile[k] = gf_xpow8((unsigned long long)kTile * (k + 1));
             return t;
         }();
         memcpy(a.crcP, tab.P, sizeof(tab.P));
-        a.crc_tile = tab.tile;
-        const size_t lens[2] = {raw % kTile, rows > 0 ? 0 : (total % (chunk ? chunk : 1)) % kTile};
-        for (int k = 0; k < 2; ++k) { a.crc_part_len[k] = (uint32_t)lens[k]; a.crc_part_mul[k] = lens[k] ? gf_xpow8(lens[k]) : 0u; }
+        memcpy(a.crc_tilek, tab.tile, sizeof(tab.tile));
     }
     {
         ProfScope prof(K_DEFLATE, stream);
+        if (rows == 0 && chunk <= 4u * kTile && total >= prefix_len + 2 * chunk) {
+            // plain mode with several chunks per source: one CTA encodes a chunk of zeros, the others copy it where they find one
+            uint8_t* tmpl = a.slots + (size_t)n * a.slot_pitch;
+            ZArgs t = a;
+            t.zero_source = 1; t.total = chunk; t.spv = 1; t.prefix = nullptr; t.prefix_len = 0; t.expand = 0;
+            t.meta = reinterpret_cast<uint32_t*>(tmpl); t.slots = tmpl + 16; t.slot_pitch = 0; t.tmpl = nullptr;
+            deflate_kernel<<<1, kZThreads, 0, stream>>>(t);
+            MSL_LAUNCH_CHECK("deflate_kernel (template)");
+            a.tmpl = tmpl;
+        }
         deflate_kernel<<<n, kZThreads, 0, stream>>>(a);
         MSL_LAUNCH_CHECK("deflate_kernel");
     }

@@ -127,6 +127,22 @@ __device__ void build_table(const uint8_t* lens, int n, uint16_t* fast, int fast
     __syncwarp();
 }
 
+// the fixed code of RFC 1951 section 3.2.6 needs no canonical construction: every look-up entry follows from its index
+__device__ void build_fixed_tables(uint16_t* lit, uint16_t* dist, int* lit_count, int* dist_count, int lane) {
+    for (int k = lane; k < (1 << kLitBits); k += 32) {
+        const uint32_t c7 = __brev((uint32_t)k & 0x7fu) >> 25, c8 = __brev((uint32_t)k & 0xffu) >> 24, c9 = __brev((uint32_t)k & 0x1ffu) >> 23;
+        uint32_t sym, l;
+        if (c7 <= 0x17u) { sym = 256u + c7; l = 7; }
+        else if (c8 >= 0x30u && c8 <= 0xbfu) { sym = c8 - 0x30u; l = 8; }
+        else if (c8 >= 0xc0u && c8 <= 0xc7u) { sym = 280u + (c8 - 0xc0u); l = 8; }
+        else { sym = 144u + (c9 - 0x190u); l = 9; }
+        lit[k] = (uint16_t)((sym << 4) | l);
+    }
+    for (int k = lane; k < (1 << kDistBits); k += 32) dist[k] = (uint16_t)(((__brev((uint32_t)k & 31u) >> 27) << 4) | 5u);
+    if (lane < 16) { lit_count[lane] = 0; dist_count[lane] = 0; }
+    __syncwarp();
+}
+
 // decode one symbol; returns -1 when no code matches
 __device__ __forceinline__ int decode_sym(BitReader& br, const uint16_t* fast, int fastbits, const int* count, const uint16_t* sorted) {
     const uint32_t e = fast[br.peek(fastbits)];
@@ -189,6 +205,14 @@ __global__ void __launch_bounds__(kInfWarps * 32) inflate_kernel(const InfArgs a
     auto flush_all = [&]() {
         flush_blocks();
         __syncwarp();
+        if (out_aligned && (flushed & 3) == 0) {
+            const unsigned nw = (unsigned)(pos - flushed) >> 2;
+            const uint32_t* r32 = reinterpret_cast<const uint32_t*>(ring);
+            uint32_t* o32 = reinterpret_cast<uint32_t*>(out + flushed);
+            const unsigned w0 = (unsigned)(flushed % kOutRing) >> 2;
+            for (unsigned w = lane; w < nw; w += 32) o32[w] = r32[(w0 + w) % (kOutRing / 4)];
+            flushed += 4ull * nw;
+        }
         for (unsigned long long k = flushed + lane; k < pos; k += 32) out[k] = ring[k % kOutRing];
         flushed = pos;
         __syncwarp();
@@ -220,44 +244,86 @@ __global__ void __launch_bounds__(kInfWarps * 32) inflate_kernel(const InfArgs a
             br.refill();
             const uint32_t bfinal = br.take(1), btype = br.take(2);
             if (btype == 0) {
-                // stored: skip to the byte boundary, LEN, NLEN, then the bytes pass through the ring like everything else
-                unsigned long long bp = (br.bitpos() + 7) >> 3;
-                if (bp + 4 > send) { err = INF_ERR_INPUT; break; }
-                const uint32_t len = a.src[bp] | ((uint32_t)a.src[bp + 1] << 8), nlen = a.src[bp + 2] | ((uint32_t)a.src[bp + 3] << 8);
+                // stored: skip to the byte boundary; LEN / NLEN come out of the bit buffer (no trip to global memory)
+                br.drop(br.nb & 7);
+                br.refill();
+                const uint32_t lw = (uint32_t)br.bb;
+                br.bb >>= 32; br.nb -= 32;
+                const unsigned long long bp = br.bitpos() >> 3;
+                if (bp > send) { err = INF_ERR_INPUT; break; }
+                const uint32_t len = lw & 0xffffu, nlen = lw >> 16;
                 if ((len ^ nlen) != 0xffffu) { err = INF_ERR_BLOCK; break; }
-                bp += 4;
                 if (bp + len > send) { err = INF_ERR_INPUT; break; }
                 if (pos + len > cap) { err = INF_ERR_SPACE; break; }
-                // what is still in the ring leaves first; then the block goes straight from the source to the output (four
-                // independent byte loads per lane in flight) and its last kOutRing bytes also into the ring, for later matches
-                flush_all();
-                for (uint32_t base = 0; base < len; base += 128) {
-                    uint32_t v[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { const uint32_t i = base + lane + 32 * k; v[k] = i < len ? a.src[bp + i] : 0u; }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t i = base + lane + 32 * k;
-                        if (i < len) {
-                            out[pos + i] = (uint8_t)v[k];
-                            if (len - i <= (uint32_t)kOutRing) ring[(pos + i) % kOutRing] = (uint8_t)v[k];
+                // an empty stored block (the byte alignment behind a fixed block) costs nothing more: decoding goes on in the bit buffer
+                if (len) {
+                    // what is still in the ring leaves first; then the block goes straight from the source to the output and its
+                    // last kOutRing bytes also into the ring, for later matches.  The first 512 bytes are loaded BEFORE the bit
+                    // reader is restarted behind the block, so that both round trips to memory overlap.
+                    flush_all();
+                    const uint8_t* sp = a.src + bp;
+                    if (out_aligned && (pos & 3) == 0) {
+                        const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(sp) & 3);
+                        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sp - mis);
+                        const unsigned long long lim = (a.src_bytes + 3) >> 2;                 // readable words at src
+                        const unsigned long long sw0 = (unsigned long long)((sp - mis) - a.src) >> 2;
+                        const uint32_t nw = len >> 2;
+                        uint32_t* o32 = reinterpret_cast<uint32_t*>(out + pos);
+                        uint32_t* r32 = reinterpret_cast<uint32_t*>(ring);
+                        const unsigned rw0 = (unsigned)(pos % kOutRing) >> 2;
+                        uint32_t lo[4], hi[4];
+    #pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t w = lane + 32 * k;
+                            lo[k] = (w < nw && sw0 + w < lim) ? __ldg(s32 + w) : 0u;
+                            hi[k] = (mis && w < nw && sw0 + w + 1 < lim) ? __ldg(s32 + w + 1) : 0u;
                         }
+                        br.init(a.src, a.src_bytes, bp + len, T.in_ring, lane);
+    #pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t w = lane + 32 * k;
+                            if (w < nw) {
+                                const uint32_t v = __funnelshift_r(lo[k], hi[k], 8 * mis);
+                                o32[w] = v;
+                                if (nw - w < (uint32_t)(kOutRing / 4)) r32[(rw0 + w) % (kOutRing / 4)] = v;
+                            }
+                        }
+                        for (uint32_t base = 128; base < nw; base += 32) {
+                            const uint32_t w = base + lane;
+                            if (w < nw) {
+                                const uint32_t l0 = sw0 + w < lim ? __ldg(s32 + w) : 0u, h0 = (mis && sw0 + w + 1 < lim) ? __ldg(s32 + w + 1) : 0u;
+                                const uint32_t v = __funnelshift_r(l0, h0, 8 * mis);
+                                o32[w] = v;
+                                if (nw - w < (uint32_t)(kOutRing / 4)) r32[(rw0 + w) % (kOutRing / 4)] = v;
+                            }
+                        }
+                        if (const uint32_t i = 4 * nw + lane; i < len) { const uint8_t v = sp[i]; out[pos + i] = v; ring[(pos + i) % kOutRing] = v; }
+                    } else {
+                        for (uint32_t base = 0; base < len; base += 128) {
+                            uint32_t v[4];
+    #pragma unroll
+                            for (int k = 0; k < 4; ++k) { const uint32_t i = base + lane + 32 * k; v[k] = i < len ? sp[i] : 0u; }
+    #pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t i = base + lane + 32 * k;
+                                if (i < len) {
+                                    out[pos + i] = (uint8_t)v[k];
+                                    if (len - i <= (uint32_t)kOutRing) ring[(pos + i) % kOutRing] = (uint8_t)v[k];
+                                }
+                            }
+                        }
+                        br.init(a.src, a.src_bytes, bp + len, T.in_ring, lane);
                     }
+                    pos += len;
+                    flushed = pos;
+                    __syncwarp();
                 }
-                pos += len;
-                flushed = pos;
-                __syncwarp();
-                br.init(a.src, a.src_bytes, bp + len, T.in_ring, lane);
             } else if (btype == 3) {
                 err = INF_ERR_BLOCK; break;
             } else {
                 if (btype == 1) {
                     if (!fixed_ready) {
-                        for (int i = lane; i < 288; i += 32) T.lens[i] = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8));
-                        if (lane < 32) T.lens[288 + lane] = 5;
-                        __syncwarp();
-                        build_table(T.lens, 288, T.lit, kLitBits, T.lit_count, T.lit_sorted, T.codes, T.next_code, T.offs, lane);
-                        build_table(T.lens + 288, 30, T.dist, kDistBits, T.dist_count, T.dist_sorted, T.codes, T.next_code, T.offs, lane);
+                        build_fixed_tables(T.lit, T.dist, T.lit_count, T.dist_count, lane);
                         fixed_ready = true;
                     }
                 } else {
@@ -327,9 +393,19 @@ __global__ void __launch_bounds__(kInfWarps * 32) inflate_kernel(const InfArgs a
                     const unsigned long long from = pos - dist;
                     if (dist + (unsigned)len <= (unsigned)kRingKeep) {
                         // the whole source lies in the ring
-                        if (dist == 1) {
-                            const uint8_t v = ring[from % kOutRing];
-                            for (int i = lane; i < len; i += 32) ring[(pos + i) % kOutRing] = v;
+                        if (dist == 1 || dist == 2 || dist == 4) {
+                            // a pattern whose period divides four: every aligned word of the destination is the same word
+                            uint32_t W = 0;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) W |= (uint32_t)ring[(from + (((unsigned)j - (unsigned)from) & (dist - 1u))) % kOutRing] << (8 * j);
+                            const unsigned head = min((unsigned)len, (4u - ((unsigned)pos & 3u)) & 3u);
+                            if ((unsigned)lane < head) ring[(pos + lane) % kOutRing] = (uint8_t)(W >> (8 * (((unsigned)pos + lane) & 3u)));
+                            const unsigned long long a0 = pos + head;
+                            const unsigned nw = ((unsigned)len - head) >> 2, tail = ((unsigned)len - head) & 3u;
+                            uint32_t* r32 = reinterpret_cast<uint32_t*>(ring);
+                            const unsigned w0 = (unsigned)(a0 % kOutRing) >> 2;
+                            for (unsigned w = lane; w < nw; w += 32) r32[(w0 + w) % (kOutRing / 4)] = W;
+                            if ((unsigned)lane < tail) ring[(a0 + 4ull * nw + lane) % kOutRing] = (uint8_t)(W >> (8 * lane));
                         } else if (dist >= (unsigned)len) {
                             for (int i = lane; i < len; i += 32) ring[(pos + i) % kOutRing] = ring[(from + i) % kOutRing];
                         } else {
@@ -389,73 +465,146 @@ __device__ __forceinline__ int paeth(int a, int b, int c) {
     return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
 }
 
-__global__ void __launch_bounds__(128) png_unfilter_kernel(const PngArgs2 a) {
-    const int lane = threadIdx.x & 31;
-    const int s = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (s >= a.n) return;
+constexpr int kUnfWarps = 8;
+
+__global__ void __launch_bounds__(kUnfWarps * 32) png_unfilter_kernel(const PngArgs2 a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = blockIdx.x;
     uint8_t* raw = a.raw + a.raw_off[s];
     const unsigned long long have = a.raw_off[s + 1] - a.raw_off[s];
     const int rb = a.W * a.bpp, bpp = a.bpp;
     uint8_t* out = a.out + (size_t)s * a.H * a.W;
-    if (have < (unsigned long long)a.H * (rb + 1)) { if (lane == 0) a.status[s] = 1; return; }
+    if (have < (unsigned long long)a.H * (rb + 1)) { if (threadIdx.x == 0) a.status[s] = 1; return; }
     uint32_t bad = 0;
     if (bpp == 1 && rb <= 256) {
-        // 8-bit gray scanlines of up to 256 bytes (the predicted masks cv2.imwrite saves): every lane keeps bytes lane, lane + 32,
-        // ... of the current and of the previous (reconstructed) scanline in registers and the next scanline's loads are issued
-        // before the current one is processed, so a row costs one memory round trip at most and no row is read twice
-        uint32_t cur[8], up[8], nxt[8];
-        int ft = raw[0], ft_next = 0;
+        // None / Sub / Up only (what cv2.imwrite's adaptive filtering picks for masks): None and Sub scanlines do not depend on
+        // their neighbours, so the CTA's warps take the rows in turn (Sub = a prefix sum along the row) and write Up rows as
+        // the differences they are; a second pass, one thread per column, adds those up going down the image.  Any Average /
+        // Paeth scanline sends the image down the serial path below, on warp 0.
+        int simple = 1, up_rows = 0;
+        for (int y0 = 0; y0 < a.H; y0 += kUnfWarps * 32)           // (warp-uniform trip count: a barrier follows)
+            if (const int y = y0 + (int)threadIdx.x; y < a.H) { const int ft = raw[(size_t)y * (rb + 1)]; simple &= ft <= 2 ? 1 : 0; up_rows |= ft == 2 ? 1 : 0; }
+        __syncwarp();
+        simple = __syncthreads_and(simple);
+        up_rows = __syncthreads_or(up_rows);
+        if (simple) {
+            for (int y = warp; y < a.H; y += kUnfWarps) {
+                const uint8_t* row = raw + (size_t)y * (rb + 1);
+                const int ft = row[0];
+                uint32_t cur[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { const int i = lane + 32 * k; up[k] = 0; cur[k] = i < rb ? raw[1 + i] : 0u; }
-        for (int y = 0; y < a.H; ++y) {
-            if (y + 1 < a.H) {
-                const uint8_t* nr = raw + (size_t)(y + 1) * (rb + 1);
-                ft_next = nr[0];
+                for (int k = 0; k < 8; ++k) { const int i = lane + 32 * k; cur[k] = i < rb ? row[1 + i] : 0u; }
+                if (ft == 1) {
+                    int carry = 0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) { const int i = lane + 32 * k; nxt[k] = i < rb ? nr[1 + i] : 0u; }
-            }
-            if (ft == 1) {              // Sub: prefix sums mod 256 along the scanline
-                int carry = 0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if (32 * k < rb) {
-                        const int v = warp_incl_scan((int)cur[k], lane) + carry;
-                        cur[k] = (uint32_t)v & 0xffu;
-                        carry = __shfl_sync(FULL, v, 31) & 0xff;
-                    }
-                }
-            } else if (ft == 2) {       // Up
-#pragma unroll
-                for (int k = 0; k < 8; ++k) cur[k] = (cur[k] + up[k]) & 0xffu;
-            } else if (ft == 3 || ft == 4) {
-                // Average / Paeth: every byte needs its reconstructed left neighbour - serial along the scanline, the
-                // neighbour handed from lane to lane
-                int left = 0, upleft = 0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if (32 * k < rb) {
-                        for (int l = 0; l < 32; ++l) {
-                            const int u = (int)up[k];
-                            int v = (int)cur[k];
-                            if (lane == l) v = (v + (ft == 3 ? ((left + u) >> 1) : paeth(left, u, upleft))) & 0xff;
-                            cur[k] = (uint32_t)v;
-                            left = __shfl_sync(FULL, v, l);
-                            upleft = __shfl_sync(FULL, u, l);
+                    for (int k = 0; k < 8; ++k) {
+                        if (32 * k < rb) {
+                            const int v = warp_incl_scan((int)cur[k], lane) + carry;
+                            cur[k] = (uint32_t)v & 0xffu;
+                            carry = __shfl_sync(FULL, v, 31) & 0xff;
                         }
                     }
                 }
-            } else if (ft != 0) bad = 1;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int i = lane + 32 * k;
-                if (i < rb) out[(size_t)y * a.W + i] = (uint8_t)cur[k];
-                up[k] = cur[k]; cur[k] = nxt[k];
+                for (int k = 0; k < 8; ++k) { const int i = lane + 32 * k; if (i < rb) out[(size_t)y * a.W + i] = (uint8_t)cur[k]; }
             }
-            ft = ft_next;
+            if (up_rows) {
+                __syncthreads();
+                if (const int x = threadIdx.x; x < rb) {
+                    uint32_t prev = 0;
+#pragma unroll 4
+                    for (int y = 0; y < a.H; ++y) {
+                        const int ft = raw[(size_t)y * (rb + 1)];
+                        uint32_t v = out[(size_t)y * a.W + x];
+                        if (ft == 2) { v = (v + prev) & 0xffu; out[(size_t)y * a.W + x] = (uint8_t)v; }
+                        prev = v;
+                    }
+                }
+            }
+            if (threadIdx.x == 0) a.status[s] = 0;
+            return;
         }
-        if (lane == 0) a.status[s] = bad;
+    }
+    if (bpp == 1 && rb <= 256) {
+        // Average / Paeth scanlines present.  A scanline filtered with None or Sub does not look at the one above it, so the
+        // image falls apart into independent chains (such a row + the Up / Average / Paeth rows that follow it); the CTA's
+        // warps take the chains in turn.  Inside a chain every lane keeps bytes lane, lane + 32, ... of the current and of the
+        // previous (reconstructed) scanline in registers and the next scanline's loads are issued before the current one is
+        // processed, so a row costs one memory round trip at most and no row is read twice.
+        if (threadIdx.x == 0) a.status[s] = 0;
+        __syncthreads();
+        auto chain = [&](int yb) {
+            uint32_t cur[8], up[8], nxt[8];
+            int ft = raw[(size_t)yb * (rb + 1)], ft_next = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const int i = lane + 32 * k; up[k] = 0; nxt[k] = 0; cur[k] = i < rb ? raw[(size_t)yb * (rb + 1) + 1 + i] : 0u; }
+            for (int y = yb; y < a.H; ++y) {
+                bool more = false;
+                if (y + 1 < a.H) {
+                    const uint8_t* nr = raw + (size_t)(y + 1) * (rb + 1);
+                    ft_next = nr[0];
+                    more = ft_next >= 2;
+                    if (more) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { const int i = lane + 32 * k; nxt[k] = i < rb ? nr[1 + i] : 0u; }
+                    }
+                }
+                if (ft == 1) {              // Sub: prefix sums mod 256 along the scanline
+                    int carry = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (32 * k < rb) {
+                            const int v = warp_incl_scan((int)cur[k], lane) + carry;
+                            cur[k] = (uint32_t)v & 0xffu;
+                            carry = __shfl_sync(FULL, v, 31) & 0xff;
+                        }
+                    }
+                } else if (ft == 2) {       // Up
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) cur[k] = (cur[k] + up[k]) & 0xffu;
+                } else if (ft == 3 || ft == 4) {
+                    // Average / Paeth: every byte needs its reconstructed left neighbour - serial along the scanline, the
+                    // neighbour handed from lane to lane
+                    int left = 0, upleft = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (32 * k < rb) {
+                            for (int l = 0; l < 32; ++l) {
+                                const int u = (int)up[k];
+                                int v = (int)cur[k];
+                                if (lane == l) v = (v + (ft == 3 ? ((left + u) >> 1) : paeth(left, u, upleft))) & 0xff;
+                                cur[k] = (uint32_t)v;
+                                left = __shfl_sync(FULL, v, l);
+                                upleft = __shfl_sync(FULL, u, l);
+                            }
+                        }
+                    }
+                } else if (ft != 0) bad = 1;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = lane + 32 * k;
+                    if (i < rb) out[(size_t)y * a.W + i] = (uint8_t)cur[k];
+                    up[k] = cur[k]; cur[k] = nxt[k];
+                }
+                ft = ft_next;
+                if (!more) break;
+            }
+        };
+        int idx = 0;
+        for (int y0 = 0; y0 < a.H; y0 += 32) {
+            const int y = y0 + lane;
+            const bool restart = y < a.H && (y == 0 || raw[(size_t)y * (rb + 1)] <= 1);
+            unsigned mask = __ballot_sync(FULL, restart);
+            while (mask) {
+                const int bsel = __ffs((int)mask) - 1;
+                mask &= mask - 1;
+                if ((idx++ & (kUnfWarps - 1)) == warp) chain(y0 + bsel);
+            }
+        }
+        if (bad && lane == 0) a.status[s] = 1;
         return;
     }
+    if (warp) return;
     for (int y = 0; y < a.H; ++y) {
         uint8_t* cur = raw + (size_t)y * (rb + 1) + 1;
         const uint8_t* up = y ? cur - (rb + 1) : nullptr;
@@ -542,7 +691,7 @@ int launch_png_unfilter(uint8_t* raw, const unsigned long long* raw_off, int n, 
     PngArgs2 a;
     a.raw = raw; a.raw_off = raw_off; a.out = out; a.n = n; a.H = H; a.W = W; a.bpp = bpp; a.status = status;
     ProfScope prof(K_PNG_UNFILTER, stream);
-    png_unfilter_kernel<<<(n + 3) / 4, 128, 0, stream>>>(a);
+    png_unfilter_kernel<<<n, kUnfWarps * 32, 0, stream>>>(a);
     MSL_LAUNCH_CHECK("png_unfilter_kernel");
     return MSL_OK;
 }

@@ -13,7 +13,7 @@ namespace msl {
 namespace {
 std::atomic<unsigned long long> g_launches[K_NKIND];
 std::atomic<bool> g_on{false};
-struct Rec { int kind; cudaEvent_t e0, e1; };
+struct Rec { int kind; cudaEvent_t e0, e1; cudaStream_t stream; };
 std::mutex g_mu;
 std::vector<Rec> g_recs;
 
@@ -39,7 +39,7 @@ ProfScope::~ProfScope() {
     if (e0_ && e1_) {
         cudaEventRecord(e1_, stream_);
         std::lock_guard<std::mutex> lk(g_mu);
-        g_recs.push_back({kind_, e0_, e1_});
+        g_recs.push_back({kind_, e0_, e1_, stream_});
     }
 }
 
@@ -71,6 +71,22 @@ int msl_profile_enable(int on) {
     }
     g_on.store(on != 0);
     return MSL_OK;
+}
+
+int msl_profile_timeline(int cap, int* kind, unsigned long long* stream, double* start_ms, double* end_ms) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int n = 0;
+    for (auto& r : g_recs) {
+        if (n >= cap) break;
+        float a = 0.f, b = 0.f;
+        if (cudaEventSynchronize(r.e1) != cudaSuccess || cudaEventElapsedTime(&a, g_recs[0].e0, r.e0) != cudaSuccess ||
+            cudaEventElapsedTime(&b, g_recs[0].e0, r.e1) != cudaSuccess) {
+            set_error("profile event failed"); return -1;
+        }
+        kind[n] = r.kind; stream[n] = (unsigned long long)reinterpret_cast<uintptr_t>(r.stream); start_ms[n] = a; end_ms[n] = b;
+        ++n;
+    }
+    return n;
 }
 
 int msl_profile_collect(double* ms_per_kind, unsigned long long* n_per_kind) {

@@ -68,6 +68,7 @@ _SIGNATURES = {
     "msl_kernel_launches": (C.c_ulonglong, [C.POINTER(C.c_ulonglong)]),
     "msl_profile_enable": (C.c_int, [_i]),
     "msl_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
+    "msl_profile_timeline": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_ulonglong), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
 _lib = None
@@ -112,6 +113,17 @@ def kernel_launches() -> dict:
 
 def profile_enable(on: bool = True) -> None:
     check(load().msl_profile_enable(1 if on else 0))
+
+
+def profile_timeline(cap: int = 1 << 16) -> list:
+    """[(kernel kind name, stream handle, start ms, end ms)] of the launches recorded since profile_enable(), in launch
+    order; call it before profile_collect()."""
+    lib = load()
+    kind = (C.c_int * cap)(); stream = (C.c_ulonglong * cap)(); t0 = (C.c_double * cap)(); t1 = (C.c_double * cap)()
+    n = lib.msl_profile_timeline(cap, kind, stream, t0, t1)
+    if n < 0:
+        raise RuntimeError(lib.msl_last_error().decode())
+    return [(lib.msl_kernel_name(kind[i]).decode(), int(stream[i]), float(t0[i]), float(t1[i])) for i in range(n)]
 
 
 def profile_collect() -> dict:
