@@ -370,10 +370,10 @@ def run_ours(args):
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     dk = kernels[dom]
     achieved = dk.get("gb_s", 0.0)
-    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/r1_traffic.json):
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/r2_traffic.json):
     # measured dram__bytes_read.sum + dram__bytes_write.sum per pixel of that capture, scaled to this launch size.
     traffic, traffic_src = None, None
-    tfile = ROOT / "profiles" / "r1_traffic.json"
+    tfile = ROOT / "profiles" / "r2_traffic.json"
     if tfile.exists():
         tj = json.loads(tfile.read_text()).get(dom)
         if tj:
@@ -647,7 +647,7 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
     Chunks of 4 patients over 3 streams; per chunk the host walks the container indexes (numpy) and, once the chunk's
     sizes have arrived, enqueues the copy of its packed result bytes."""
     from mslesseg_b200 import codec
-    B, CH, nstream = args.batch, 4, 3
+    B, CH, nstream = args.batch, int(os.environ.get("MSL_E2E_CH", "4")), int(os.environ.get("MSL_E2E_STREAMS", "3"))
     X, Y, Z = S.SHAPE_XYZ
     N = X * Y * Z
     aff = np.diag([1.0, 1.0, 1.0, 1.0])
@@ -726,6 +726,10 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
     hdr_f32 = torch.from_numpy(np.frombuffer(codec.nifti_header_bytes((X, Y, Z), np.float32, aff), np.uint8).copy()).to(device)
     hdr_u8 = torch.from_numpy(np.frombuffer(codec.nifti_header_bytes((X, Y, Z), np.uint8, aff), np.uint8).copy()).to(device)
     h2d = d2h = 0
+    # MSL_E2E_MAPPED=1: the pack kernels store straight into the pinned (mapped) host buffers instead of packing on the device
+    # and copying each stack once its size is on the host.  Measured slower (44.5 vs 37.1 ms per step): the pack kernels then
+    # run at the speed of the host link (35 GB/s) and keep their SM slots for that long.
+    mapped = os.environ.get("MSL_E2E_MAPPED") is not None
     waits = [0.0]            # seconds the host spent blocked on the chunk events (the rest of a step is enqueue work)
 
     def member_offsets(H, c0, n, pitch):
@@ -806,12 +810,14 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
             for k, pl in enumerate(PLANOS):
                 n_p, rows, cols = dims[pl]
                 px = d["outs4"][pl] if n == CH else torch.stack([o[(m, pl)] for m in MEJORAS])
-                res[pl] = ops.png_encode(px.reshape(-1, cols, rows), out=d["png_out"][pl], workspace=d["png_ws"])
+                res[pl] = ops.png_encode(px.reshape(-1, cols, rows), out=h_png[pl][hi] if mapped else d["png_out"][pl], workspace=d["png_ws"])
                 d["d_tot"][k:k + 1].copy_(res[pl].off[-1:], non_blocking=True)
+            third = d["gz_out"].numel() // 3
+            gz_dst = h_gz[hi] if mapped else d["gz_out"]
             res["gz"] = [ops.deflate_files(d["rvol"][pl][:n], prefix=hdr_f32, expand_u8_to_f32=True, chunk_len=codec.CHUNK, container="gzip",
-                                           dist2=4, workspace=d["gz_ws"],
-                                           out=d["gz_out"][k * (d["gz_out"].numel() // 3):(k + 1) * (d["gz_out"].numel() // 3)]) for k, pl in enumerate(PLANOS)]
-            res["gz8"] = ops.deflate_files(cons, prefix=hdr_u8, chunk_len=codec.CHUNK, container="gzip", dist2=0, out=d["gz8_out"], workspace=d["gz_ws"])
+                                           dist2=4, workspace=d["gz_ws"], out=gz_dst[k * third:(k + 1) * third]) for k, pl in enumerate(PLANOS)]
+            res["gz8"] = ops.deflate_files(cons, prefix=hdr_u8, chunk_len=codec.CHUNK, container="gzip", dist2=0,
+                                           out=h_gz8[hi] if mapped else d["gz8_out"], workspace=d["gz_ws"])
             for k in range(3):
                 d["d_tot"][3 + k:4 + k].copy_(res["gz"][k].off[-1:], non_blocking=True)
             d["d_tot"][6:7].copy_(res["gz8"].off[-1:], non_blocking=True)
@@ -826,10 +832,24 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
         """The chunk's sizes are on the host: enqueue the copies of exactly the bytes its files occupy (+ offsets, status)."""
         nonlocal d2h
         st, d = streams[ci % nstream], slots[ci % nstream]
+        res, o, cons, srow, flags, n, hi = d["keep"]
+        if mapped and not count and d2h_events is None:
+            # the packed files were written into the pinned host buffers by the pack kernels themselves: only the small
+            # tables are left to copy, and nothing here needs the sizes (no host synchronisation per chunk)
+            with torch.cuda.stream(st):
+                for k, pl in enumerate(PLANOS):
+                    h_off[pl][hi][:res[pl].off.numel()].copy_(res[pl].off, non_blocking=True)
+                for k in range(3):
+                    h_off["gz"][hi][k][:res["gz"][k].off.numel()].copy_(res["gz"][k].off, non_blocking=True)
+                h_off["gz8"][hi][:res["gz8"].off.numel()].copy_(res["gz8"].off, non_blocking=True)
+                h_status[hi][:srow].copy_(d["status"][:srow], non_blocking=True)
+                h_inexact[hi].copy_(d["inexact"], non_blocking=True)
+                n_status[hi] = srow
+                d["done"].record(st)
+            return
         tw = time.perf_counter()
         d["event"].synchronize()
         waits[0] += time.perf_counter() - tw
-        res, o, cons, srow, flags, n, hi = d["keep"]
         tot = d["h_tot"].numpy()
         with torch.cuda.stream(st):
             moved = 0
@@ -838,17 +858,20 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
                 d2h_events[-1][0].record(st)
             for k, pl in enumerate(PLANOS):
                 t = int(tot[k])
-                h_png[pl][hi][:t].copy_(res[pl].data[:t], non_blocking=True)
+                if not mapped:
+                    h_png[pl][hi][:t].copy_(res[pl].data[:t], non_blocking=True)
                 h_off[pl][hi][:res[pl].off.numel()].copy_(res[pl].off, non_blocking=True)
                 moved += t + res[pl].off.numel() * 8
             third = d["gz_out"].numel() // 3
             for k in range(3):
                 t = int(tot[3 + k])
-                h_gz[hi][k * third:k * third + t].copy_(res["gz"][k].data[:t], non_blocking=True)
+                if not mapped:
+                    h_gz[hi][k * third:k * third + t].copy_(res["gz"][k].data[:t], non_blocking=True)
                 h_off["gz"][hi][k][:res["gz"][k].off.numel()].copy_(res["gz"][k].off, non_blocking=True)
                 moved += t + res["gz"][k].off.numel() * 8
             t = int(tot[6])
-            h_gz8[hi][:t].copy_(res["gz8"].data[:t], non_blocking=True)
+            if not mapped:
+                h_gz8[hi][:t].copy_(res["gz8"].data[:t], non_blocking=True)
             h_off["gz8"][hi][:res["gz8"].off.numel()].copy_(res["gz8"].off, non_blocking=True)
             h_status[hi][:srow].copy_(d["status"][:srow], non_blocking=True)
             h_inexact[hi].copy_(d["inexact"], non_blocking=True)
@@ -899,10 +922,13 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
     e2e_step()
     sync_all()
     d2h_ms = sum(a_.elapsed_time(b_) for a_, b_, _ in d2h_events)
-    d2h_gbs = sum(m_ for _, _, m_ in d2h_events) / max(d2h_ms, 1e-9) / 1e6
+    d2h_moved = sum(m_ for _, _, m_ in d2h_events)
     d2h_events = None
     tl = _L2.profile_timeline()
     kern = {k: round(v[0], 3) for k, v in sorted(_L2.profile_collect().items(), key=lambda kv: -kv[1][0])}
+    if mapped:                # the result bytes cross the link inside the pack kernels
+        d2h_ms = kern.get("deflate_pack", 0.0)
+    d2h_gbs = d2h_moved / max(d2h_ms, 1e-9) / 1e6
     # union of the kernel intervals of that step = time during which at least one of this library's kernels was running
     busy, end = 0.0, -1.0
     for _, _, a_, b_ in sorted(tl, key=lambda r: r[2]):
@@ -952,7 +978,9 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
             "kernel_ms_per_step": kern, "d2h_copy_ms_per_step": round(d2h_ms, 3), "d2h_copy_gb_s": round(d2h_gbs, 1), "kernel_busy_ms_per_step": round(busy, 3), "kernel_span_ms_per_step": round(span, 3), "host_enqueue_ms_per_step": host_enqueue_ms,
             "note": ("host buffers hold FILES: .nii.gz volumes (FLAIR float32, GT float32) and predicted-mask PNGs in; PNG slices of the 12 "
                      "stacks, float32 .nii.gz of the 3 reconstructions, uint8 consensus .nii.gz and the count table out; inflate / "
-                     "deflate on the GPU; 4-patient chunks over 3 streams; wall clock around synchronised steps")}
+                     f"deflate on the GPU; {CH}-patient chunks over {nstream} streams; wall clock around synchronised steps; "
+                     + ("the packed files are written into the pinned host buffers by the pack kernels (mapped memory), d2h_copy_* = those kernels"
+                        if mapped else "packed on the device, one copy per stack once its size is on the host"))}
 
 
 _REAL_STDOUT = None

@@ -22,6 +22,8 @@
 // scan_sizes_kernel + pack_kernel: the variable-length streams are packed back to back (exclusive scan of the sizes) into
 //   one buffer = one D2H copy; PNG's IDAT CRC-32 (over the compressed bytes) is computed during the copy.
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "msl_common.cuh"
 #include "msl_kernels.h"
@@ -41,6 +43,7 @@ constexpr int kTile = kZThreads * kSeg;          // 4 KB
 constexpr int kLook = 16;                        // look-back kept in front of the tile (>= the largest match distance)
 constexpr int kYBytes = 16 + kTile + kTile / 2 + 128;   // staging: carry + worst case (every other 16-byte segment its own stored block) + trailer
 constexpr uint32_t kCrcPoly = 0xedb88320u;       // reflected CRC-32 polynomial
+constexpr int kTmplBytes = 400;                  // stream of an all-zero chunk of up to four tiles (378 bytes as a gzip member)
 
 // a * b mod P over GF(2), operands in the reflected representation CRC-32 uses (bit 31 = x^0)
 __host__ __device__ inline uint32_t gf_mul(uint32_t a, uint32_t b) {
@@ -79,18 +82,36 @@ struct ZArgs {
     uint32_t* meta;            // [n][4]: container bytes in the slot, raw bytes, checksum of the raw bytes, offset of the IDAT chunk type
     uint32_t crcP[kZThreads];  // x^(8 * kSeg * k): what a thread's 16-byte CRC is multiplied by when k segments follow it in the tile
     uint32_t crc_tilek[4];     // x^(8 * kTile * (k + 1)): k + 1 all-zero tiles
-    const uint8_t* tmpl;       // plain mode: the stream of one full all-zero chunk ([0, 16): its meta row, [16, ..): its bytes), or NULL
-    int zero_source;           // the launch that builds the template: every raw byte reads as zero
+    uint32_t tmpl_meta[4];     // plain mode: the stream of one full all-zero chunk (built on the host): its meta row ([0] = 0: none) ...
+    uint32_t tmpl[kTmplBytes / 4];   // ... and its bytes
 };
 
 __device__ __forceinline__ unsigned hdr_len_of(int container) {
     return (0x2b180200u >> (8 * (container & 3))) & 0xffu;       // raw 0, zlib 2, gzip 24, PNG 43 (no jump table)
 }
 
-__device__ __forceinline__ uint32_t rev_bits(uint32_t v, int n) { return __brev(v) >> (32 - n); }
+__host__ __device__ inline uint32_t brev32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __brev(v);
+#else
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4);
+    v = ((v >> 8) & 0x00ff00ffu) | ((v & 0x00ff00ffu) << 8);
+    return (v >> 16) | (v << 16);
+#endif
+}
+__host__ __device__ inline int clz32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __clz((int)v);
+#else
+    return v ? __builtin_clz(v) : 32;
+#endif
+}
+__host__ __device__ inline uint32_t rev_bits(uint32_t v, int n) { return brev32(v) >> (32 - n); }
 
 // fixed Huffman code of a literal / length symbol (RFC 1951 section 3.2.6), already bit-reversed; returns the bit count
-__device__ __forceinline__ int fixed_litlen(uint32_t sym, uint32_t& code) {
+__host__ __device__ inline int fixed_litlen(uint32_t sym, uint32_t& code) {
     if (sym < 144) { code = rev_bits(0x30 + sym, 8); return 8; }
     if (sym < 256) { code = rev_bits(0x190 + (sym - 144), 9); return 9; }
     if (sym < 280) { code = rev_bits(sym - 256, 7); return 7; }
@@ -98,13 +119,13 @@ __device__ __forceinline__ int fixed_litlen(uint32_t sym, uint32_t& code) {
 }
 
 // One match of `len` bytes (3..258) at distance d (1..4: distance codes 0..3, no extra bits): its bits, LSB first
-__device__ __forceinline__ int match_bits(int len, int d, uint32_t& pat) {
+__host__ __device__ inline int match_bits(int len, int d, uint32_t& pat) {
     uint32_t sym, eb = 0, ev = 0;
     if (len == 258) sym = 285;
     else {
         const uint32_t l = (uint32_t)len - 3;
         if (l < 8) sym = 257 + l;
-        else { eb = 29 - __clz(l); sym = 257 + 4 * (eb + 1) + ((l >> eb) & 3); ev = l & ((1u << eb) - 1); }
+        else { eb = 29 - clz32(l); sym = 257 + 4 * (eb + 1) + ((l >> eb) & 3); ev = l & ((1u << eb) - 1); }
     }
     uint32_t code;
     const int n = fixed_litlen(sym, code);
@@ -115,7 +136,7 @@ __device__ __forceinline__ int match_bits(int len, int d, uint32_t& pat) {
 // A run of 16 * (k + 1) bytes (k = 0..31: whole segments of one warp) as ONE fixed-Huffman block: header (BFINAL 0, BTYPE 01),
 // one or two matches (258 + the rest: the rest of a multiple of 16 is never 1 or 2), end of block.  Bits 0..47 hold the
 // block LSB first, bits 48..55 its length in bits (at most 3 + 13 + 18 + 7).
-__device__ __forceinline__ unsigned long long run_block(int k, int d) {
+__host__ __device__ inline unsigned long long run_block(int k, int d) {
     const int bytes = kSeg * (k + 1);
     unsigned long long acc = 2u;
     int n = 3;
@@ -297,7 +318,7 @@ __device__ __forceinline__ uint4 load_seg(const ZArgs& a, const uint8_t* __restr
                                           bool image, unsigned rl, unsigned rl_magic, unsigned long long r0, unsigned tb, unsigned n, int tid) {
     uint32_t w[4] = {0u, 0u, 0u, 0u};
     const unsigned b = tb + (unsigned)(kSeg * tid);
-    if (b < n && !a.zero_source) {
+    if (b < n) {
         const unsigned cnt = min((unsigned)kSeg, n - b);
         if (image) {
             const unsigned r = __umulhi(b, rl_magic), c0 = b - r * rl;
@@ -442,9 +463,9 @@ __global__ void __launch_bounds__(kZThreads, 4) deflate_kernel(const ZArgs a) {
     uint32_t crc_run = 0;                               // thread 0: running CRC-32 (zero-register form) and all-zero tiles not yet applied
     int crc_pend = 0;
     uint4 P = load_seg(a, src, pfx, plen, image, rl, rl_magic, r0, 0u, n, tid);
-    if (a.tmpl && !image && n == a.chunk && n <= 4u * kTile && r0 >= plen) {
+    if (a.tmpl_meta[0] && !image && n == a.chunk && r0 >= plen) {
         // A full chunk without header bytes: when every byte of it is zero (two thirds of a skull-stripped volume, nearly all of a
-        // mask) its stream is the same for every such chunk - built once per launch, copied here
+        // mask) its stream is the same for every such chunk - built once on the host (zero_chunk_stream), copied here
         uint32_t nz = P.x | P.y | P.z | P.w;
         for (unsigned tb = kTile; tb < n; tb += kTile) {
             const uint4 q = load_seg(a, src, pfx, plen, image, rl, rl_magic, r0, tb, n, tid);
@@ -452,12 +473,10 @@ __global__ void __launch_bounds__(kZThreads, 4) deflate_kernel(const ZArgs a) {
         }
         __syncwarp();
         if (!__syncthreads_or(nz != 0)) {
-            const uint32_t* tm = reinterpret_cast<const uint32_t*>(a.tmpl);
-            const unsigned fsize = tm[0];
-            const uint4* t4 = reinterpret_cast<const uint4*>(a.tmpl + 16);
-            uint4* d4 = reinterpret_cast<uint4*>(slot);
-            for (unsigned q0_ = 0; q0_ < ((fsize + 15) >> 4); q0_ += kZThreads) if (const unsigned q = q0_ + (unsigned)tid; q < ((fsize + 15) >> 4)) d4[q] = t4[q];
-            if (tid < 4) a.meta[4 * (size_t)s + tid] = tm[tid];
+            const unsigned fsize = a.tmpl_meta[0];
+            uint32_t* d32 = reinterpret_cast<uint32_t*>(slot);
+            if (tid < (int)((fsize + 3) >> 2)) d32[tid] = a.tmpl[tid];
+            if (tid < 4) a.meta[4 * (size_t)s + tid] = a.tmpl_meta[tid];
             return;
         }
     }
@@ -644,14 +663,12 @@ struct PackArgs {
     unsigned long long out_cap;
     uint32_t P64[kZThreads];   // x^(8 * 64 * k)
     uint32_t x16k;             // x^(8 * 16384)
+    int n;
 };
 
-__global__ void __launch_bounds__(kZThreads) pack_kernel(const PackArgs a) {
-    __shared__ uint32_t crc_table[4][256];
-    __shared__ uint32_t part[kZThreads / 32];
-    __shared__ uint32_t s_run;
+// one stream: slot -> out + off[s]
+__device__ __forceinline__ void pack_stream(const PackArgs& a, unsigned s, uint32_t (*crc_table)[256], uint32_t* part, uint32_t& s_run) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned s = blockIdx.x;
     const uint8_t* slot = a.slots + (size_t)s * a.slot_pitch;
     const uint32_t fsize = a.meta[4 * (size_t)s], idat = a.meta[4 * (size_t)s + 3];
     const unsigned long long o = a.off[s];
@@ -660,7 +677,6 @@ __global__ void __launch_bounds__(kZThreads) pack_kernel(const PackArgs a) {
     uint32_t clen = 0;                                      // PNG: bytes the IDAT CRC covers = "IDAT" + zlib stream
     if (idat) {
         clen = fsize - idat - 16;                           // file = ... [idat - 4: length][idat: "IDAT" + data][CRC][IEND chunk: 12]
-        crc_tables(crc_table, tid);
         if (tid == 0) s_run = 0;
     }
     // destination words; the source (16-byte aligned slots) is read as aligned words and shifted into place
@@ -744,6 +760,73 @@ __global__ void __launch_bounds__(kZThreads) pack_kernel(const PackArgs a) {
     }
 }
 
+// Grid-stride over the streams: a bounded number of CTAs, so that a launch whose destination is mapped HOST memory (the copy
+// then runs at the speed of the host link) leaves most of every SM to the kernels of other CUDA streams.
+__global__ void __launch_bounds__(kZThreads) pack_kernel(const PackArgs a) {
+    __shared__ uint32_t crc_table[4][256];
+    __shared__ uint32_t part[kZThreads / 32];
+    __shared__ uint32_t s_run;
+    crc_tables(crc_table, threadIdx.x);
+    block_sync();
+    for (unsigned s = blockIdx.x; s < (unsigned)a.n; s += gridDim.x) {
+        pack_stream(a, s, crc_table, part, s_run);
+        block_sync();
+    }
+}
+
+// The stream deflate_kernel produces for a chunk of n zero bytes (n = 1..4 whole tiles), restated on the host: tile 0 opens with
+// a stored block of the first segment (nothing to refer back to), then every warp's run of segments is one fixed block + the
+// empty stored block that realigns it.  Cached per (container, distance, n).
+void zero_chunk_stream(int container, int d, unsigned n, uint32_t meta[4], uint8_t* out) {
+    struct Entry { int container, d; unsigned n; uint32_t meta[4]; uint8_t bytes[kTmplBytes]; };
+    static std::mutex mu;
+    static std::vector<Entry> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    for (const Entry& e : cache)
+        if (e.container == container && e.d == d && e.n == n) { memcpy(meta, e.meta, sizeof(e.meta)); memcpy(out, e.bytes, kTmplBytes); return; }
+    Entry e;
+    memset(&e, 0, sizeof(e));
+    e.container = container; e.d = d; e.n = n;
+    uint8_t* b = e.bytes;
+    unsigned p = 0;
+    if (container == MSL_Z_ZLIB) { b[0] = 0x78; b[1] = 0x01; p = 2; }
+    else if (container == MSL_Z_GZIP) {
+        const uint8_t h[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 12, 0, 'M', 'S', 8, 0};
+        memcpy(b, h, 16); p = 24;
+    }
+    auto put_run = [&](int nl) {               // a run of nl segments: fixed block, empty stored block behind it
+        const unsigned long long blk = run_block(nl - 1, d);
+        const int hbits = (int)(blk >> 48), nb1 = (hbits + 3 + 7) >> 3;
+        for (int i = 0; i < nb1; ++i) b[p++] = (uint8_t)((blk & 0xffffffffffffull) >> (8 * i));
+        b[p++] = 0; b[p++] = 0; b[p++] = 0xff; b[p++] = 0xff;
+    };
+    for (unsigned t = 0; t < n / kTile; ++t) {
+        for (int w = 0; w < kZThreads / 32; ++w) {
+            if (t == 0 && w == 0) {
+                b[p++] = 0; b[p++] = kSeg; b[p++] = 0; b[p++] = (uint8_t)~kSeg; b[p++] = 0xff;
+                p += kSeg;                      // the sixteen zero bytes themselves
+                put_run(31);
+            } else put_run(32);
+        }
+    }
+    b[p++] = 1; b[p++] = 0; b[p++] = 0; b[p++] = 0xff; b[p++] = 0xff;
+    uint32_t chk = 0;
+    if (container == MSL_Z_ZLIB) {
+        chk = ((n % 65521u) << 16) | 1u;
+        b[p++] = chk >> 24; b[p++] = chk >> 16; b[p++] = chk >> 8; b[p++] = chk;
+    } else if (container == MSL_Z_GZIP) {
+        uint32_t c = 0xffffffffu;
+        for (unsigned i = 0; i < n; ++i) for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ kCrcPoly : c >> 1;
+        chk = ~c;
+        for (int i = 0; i < 4; ++i) b[p++] = (uint8_t)(chk >> (8 * i));
+        for (int i = 0; i < 4; ++i) b[p++] = (uint8_t)(n >> (8 * i));
+        for (int i = 0; i < 4; ++i) { b[16 + i] = (uint8_t)(p >> (8 * i)); b[20 + i] = (uint8_t)(n >> (8 * i)); }
+    }
+    e.meta[0] = p; e.meta[1] = n; e.meta[2] = chk; e.meta[3] = 0;
+    cache.push_back(e);
+    memcpy(meta, e.meta, sizeof(e.meta)); memcpy(out, e.bytes, kTmplBytes);
+}
+
 inline size_t raw_len_of(size_t chunk, int rows, int row_bytes) { return rows > 0 ? (size_t)rows * ((size_t)row_bytes + 1) : chunk; }
 
 }  // namespace
@@ -794,19 +877,11 @@ int launch_deflate_pack(const uint8_t* src, int n, size_t src_pitch, size_t chun
         }();
         memcpy(a.crcP, tab.P, sizeof(tab.P));
         memcpy(a.crc_tilek, tab.tile, sizeof(tab.tile));
+        if (rows == 0 && container != MSL_Z_PNG && chunk % kTile == 0 && chunk <= 4u * kTile && total >= prefix_len + 2 * chunk)
+            zero_chunk_stream(container, dist2 ? dist2 : 1, (unsigned)chunk, a.tmpl_meta, reinterpret_cast<uint8_t*>(a.tmpl));
     }
     {
         ProfScope prof(K_DEFLATE, stream);
-        if (rows == 0 && chunk <= 4u * kTile && total >= prefix_len + 2 * chunk) {
-            // plain mode with several chunks per source: one CTA encodes a chunk of zeros, the others copy it where they find one
-            uint8_t* tmpl = a.slots + (size_t)n * a.slot_pitch;
-            ZArgs t = a;
-            t.zero_source = 1; t.total = chunk; t.spv = 1; t.prefix = nullptr; t.prefix_len = 0; t.expand = 0;
-            t.meta = reinterpret_cast<uint32_t*>(tmpl); t.slots = tmpl + 16; t.slot_pitch = 0; t.tmpl = nullptr;
-            deflate_kernel<<<1, kZThreads, 0, stream>>>(t);
-            MSL_LAUNCH_CHECK("deflate_kernel (template)");
-            a.tmpl = tmpl;
-        }
         deflate_kernel<<<n, kZThreads, 0, stream>>>(a);
         MSL_LAUNCH_CHECK("deflate_kernel");
     }
@@ -832,7 +907,8 @@ int launch_deflate_pack(const uint8_t* src, int n, size_t src_pitch, size_t chun
             memcpy(pa.P64, tab.P, sizeof(tab.P));
             pa.x16k = tab.x16k;
         }
-        pack_kernel<<<n, kZThreads, 0, stream>>>(pa);
+        pa.n = n;
+        pack_kernel<<<n < 148 * 8 ? n : 148 * 8, kZThreads, 0, stream>>>(pa);
         MSL_LAUNCH_CHECK("pack_kernel");
     }
     if (out_meta) MSL_CUDA_CHECK(cudaMemcpyAsync(out_meta, a.meta, (size_t)n * 16, cudaMemcpyDeviceToDevice, stream));

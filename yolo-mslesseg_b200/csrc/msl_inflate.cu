@@ -645,6 +645,29 @@ template <typename T> __device__ __forceinline__ double load_unaligned(const uin
     return (double)v;
 }
 
+// float32 payload, no scaling, aligned buffers, nvox a multiple of four (the volumes of this path): 128-bit loads and stores
+__global__ void nifti_convert_f32_kernel(const float4* __restrict__ payload, unsigned long long nquad, float4* __restrict__ out_f32,
+                                         uint32_t* __restrict__ out_u8, unsigned long long* inexact) {
+    unsigned bad = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nquad; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(payload + i);
+        if (out_f32) out_f32[i] = v;
+        else {
+            const float f[4] = {v.x, v.y, v.z, v.w};
+            uint32_t w = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int q = (f[k] >= 0.0f && f[k] <= 255.0f) ? (int)f[k] : 0;
+                w |= (uint32_t)q << (8 * k);
+                bad += (float)q != f[k] ? 1u : 0u;
+            }
+            out_u8[i] = w;
+        }
+    }
+    bad = __reduce_add_sync(FULL, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(inexact, (unsigned long long)bad);
+}
+
 __global__ void nifti_convert_kernel(const uint8_t* payload, int datatype, unsigned long long nvox, double slope, double inter, int scaled,
                                      float* out_f32, uint8_t* out_u8, double* out_f64, unsigned long long* inexact) {
     unsigned long long bad = 0;
@@ -701,6 +724,13 @@ int launch_nifti_convert(const uint8_t* payload, int datatype, unsigned long lon
     if (nvox == 0) return MSL_OK;
     ProfScope prof(K_NIFTI_CONVERT, stream);
     const int blocks = (int)((nvox + 256ull * 8 - 1) / (256ull * 8) < 148 * 16 ? (nvox + 256ull * 8 - 1) / (256ull * 8) : 148 * 16);
+    if (datatype == 16 && !scaled && !out_f64 && (nvox & 3) == 0 && (reinterpret_cast<uintptr_t>(payload) & 15) == 0 &&
+        (out_f32 ? (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0 : (reinterpret_cast<uintptr_t>(out_u8) & 3) == 0) && (out_f32 != nullptr) != (out_u8 != nullptr)) {
+        nifti_convert_f32_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(payload), nvox / 4, reinterpret_cast<float4*>(out_f32),
+                                                             reinterpret_cast<uint32_t*>(out_u8), inexact);
+        MSL_LAUNCH_CHECK("nifti_convert_f32_kernel");
+        return MSL_OK;
+    }
     nifti_convert_kernel<<<blocks, 256, 0, stream>>>(payload, datatype, nvox, slope, inter, scaled, out_f32, out_u8, out_f64, inexact);
     MSL_LAUNCH_CHECK("nifti_convert_kernel");
     return MSL_OK;
