@@ -647,7 +647,7 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
     Chunks of 4 patients over 3 streams; per chunk the host walks the container indexes (numpy) and, once the chunk's
     sizes have arrived, enqueues the copy of its packed result bytes."""
     from mslesseg_b200 import codec
-    B, CH, nstream = args.batch, int(os.environ.get("MSL_E2E_CH", "4")), int(os.environ.get("MSL_E2E_STREAMS", "3"))
+    B, CH, nstream = args.batch, int(os.environ.get("MSL_E2E_CH", "4")), int(os.environ.get("MSL_E2E_STREAMS", "4"))
     X, Y, Z = S.SHAPE_XYZ
     N = X * Y * Z
     aff = np.diag([1.0, 1.0, 1.0, 1.0])
@@ -849,7 +849,8 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
             return
         tw = time.perf_counter()
         d["event"].synchronize()
-        waits[0] += time.perf_counter() - tw
+        if inline:
+            waits[0] += time.perf_counter() - tw
         tot = d["h_tot"].numpy()
         with torch.cuda.stream(st):
             moved = 0
@@ -886,15 +887,60 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
 
     d2h_events = None        # profile pass: CUDA events around every chunk's device-to-host copies
 
+    # A chunk's copies can only be enqueued once its sizes are on the host.  A helper thread waits for that (the wait releases
+    # the GIL) and enqueues them, so that the main thread keeps enqueueing the next chunks: up to `nstream` chunks are in flight
+    # and the latency-bound kernels of one chunk overlap the wide kernels of another.  MSL_E2E_INLINE=1: everything on one thread.
+    import queue
+    inline = os.environ.get("MSL_E2E_INLINE") is not None
+    work_q = queue.Queue()
+    pending = [None] * nstream          # per slot: threading.Event set when the slot's copies have been enqueued
+    worker_err = []
+
+    def worker():
+        torch.cuda.set_device(device)
+        while True:
+            item = work_q.get()
+            if item is None:
+                return
+            ci_, c0_, count_, ev_ = item
+            try:
+                deliver(ci_, c0_, count_)
+            except BaseException as ex:      # noqa: BLE001 - reported by the main thread
+                worker_err.append(ex)
+            ev_.set()
+
+    if not inline:
+        threading.Thread(target=worker, daemon=True).start()
+
+    def drain():
+        for ev_ in pending:
+            if ev_ is not None:
+                ev_.wait()
+        if worker_err:
+            raise worker_err[0]
+
     def e2e_step(count=False):
         chunks = list(enumerate(range(0, B, CH)))
-        for i, (ci, c0) in enumerate(chunks):
+        if inline:
+            for i, (ci, c0) in enumerate(chunks):
+                compute(ci, c0, count)
+                if i > 0:
+                    deliver(*chunks[i - 1], count)
+            deliver(*chunks[-1], count)
+            return
+        for ci, c0 in chunks:
+            sl = ci % nstream
+            if pending[sl] is not None:
+                tw = time.perf_counter()
+                pending[sl].wait()
+                waits[0] += time.perf_counter() - tw
             compute(ci, c0, count)
-            if i > 0:
-                deliver(*chunks[i - 1], count)
-        deliver(*chunks[-1], count)
+            pending[sl] = threading.Event()
+            work_q.put((ci, c0, count, pending[sl]))
 
     def sync_all():
+        if not inline:
+            drain()
         for st in streams:
             st.synchronize()
         if world > 1:
@@ -978,7 +1024,7 @@ def run_e2e_files(args, torch, dist, ops, S, device, world, flair, gt, preds):
             "kernel_ms_per_step": kern, "d2h_copy_ms_per_step": round(d2h_ms, 3), "d2h_copy_gb_s": round(d2h_gbs, 1), "kernel_busy_ms_per_step": round(busy, 3), "kernel_span_ms_per_step": round(span, 3), "host_enqueue_ms_per_step": host_enqueue_ms,
             "note": ("host buffers hold FILES: .nii.gz volumes (FLAIR float32, GT float32) and predicted-mask PNGs in; PNG slices of the 12 "
                      "stacks, float32 .nii.gz of the 3 reconstructions, uint8 consensus .nii.gz and the count table out; inflate / "
-                     f"deflate on the GPU; {CH}-patient chunks over {nstream} streams; wall clock around synchronised steps; "
+                     f"deflate on the GPU; {CH}-patient chunks over {nstream} streams, a helper thread enqueues a chunk's copies once its sizes are on the host; wall clock around synchronised steps; "
                      + ("the packed files are written into the pinned host buffers by the pack kernels (mapped memory), d2h_copy_* = those kernels"
                         if mapped else "packed on the device, one copy per stack once its size is on the host"))}
 
