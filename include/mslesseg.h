@@ -322,6 +322,11 @@ int                msl_kernel_kinds(void);
 const char*        msl_kernel_name(int kind);
 unsigned long long msl_kernel_launches(unsigned long long* per_kind);
 int                msl_profile_enable(int on);
+/* Self-test of the E1 division (utils/utils.py:403, f32 (corte - min) / ptp): the kernels replace it by a reciprocal hoisted
+ * per slice + a correction step; this entry runs that sequence on n device (g, p) pairs with 1e-18 <= p <= 1e18 and
+ * 0 <= g <= p (others are skipped) and returns out4 = {normal quotients that differ from the IEEE division, output bytes that
+ * differ, bytes of the packed two-voxel path that differ from the scalar one, pairs looked at} (device, uint64[4]). */
+int                msl_selftest_norm_division(const float* g, const float* p, size_t n, unsigned long long* out4, msl_stream_t stream);
 int                msl_profile_timeline(int cap, int* kind, unsigned long long* stream, double* start_ms, double* end_ms);
 int                msl_profile_collect(double* ms_per_kind, unsigned long long* n_per_kind);
 

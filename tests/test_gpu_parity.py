@@ -599,3 +599,57 @@ def test_slice_ranges_equal_numpy_min_max(cuda_device):
             assert np.array_equal(got[..., 0], v.min(axis=axis)) and np.array_equal(got[..., 1], v.max(axis=axis))
         g = r["axial"][1].cpu().numpy()
         assert M.calcular_rango_global(g, [0, 5, 9]) == (min(v[1, i].min() for i in (0, 5, 9)), max(v[1, i].max() for i in (0, 5, 9)))
+
+
+def test_norm_division_selftest(ops, torch_mod, cuda_device):
+    """E1 replaces f32(g / ptp) (reference utils/utils.py:403) by a reciprocal hoisted per slice + a correction step.  The
+    sequence has to be correctly rounded for every pair the path can produce (0 <= g <= ptp, ptp inside the guard range): it is
+    compared with the IEEE division bit for bit on the edge cases and on 10^8 random pairs."""
+    import ctypes
+    torch = torch_mod
+    from mslesseg_b200 import _lib
+    lib = _lib.load()
+
+    def run(g, p):
+        g = g.to(device=cuda_device, dtype=torch.float32).contiguous()
+        p = p.to(device=cuda_device, dtype=torch.float32).contiguous()
+        out = torch.zeros(4, dtype=torch.int64, device=cuda_device)
+        _lib.check(lib.msl_selftest_norm_division(g.data_ptr(), p.data_ptr(), g.numel(), out.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return [int(v) for v in out.cpu()]
+
+    # edge cases: all-ones mantissas, powers of two, both guard bounds, g == p, g one ulp below p, tiny / subnormal g, g == 0
+    exps = torch.arange(-59, 60, dtype=torch.float64)
+    ones = (2.0 - 2.0 ** -23) * 2.0 ** exps
+    pows = 2.0 ** exps
+    bounds = torch.tensor([1.0e-18, 1.0e18], dtype=torch.float32).double()
+    pp = torch.cat([ones, pows, bounds, torch.tensor([1.0, 3.0, 255.0, 65535.0, 1.0 / 3.0], dtype=torch.float64)]).float()
+    pp = pp[(pp >= 1.0e-18) & (pp <= 1.0e18)]
+    gs, ps = [], []
+    for frac in (1.0, 0.5, 1.0 / 3.0, 2.0 / 3.0, 1.0 / 255.0, 254.0 / 255.0, 0.999999, 1e-7, 0.0):
+        gs.append((pp.double() * frac).float().minimum(pp)); ps.append(pp)
+    gs.append(torch.nextafter(pp, torch.zeros_like(pp))); ps.append(pp)                      # one ulp below p
+    gs.append(torch.full_like(pp, 1.0e-45)); ps.append(pp)                                   # subnormal g
+    gs.append(torch.full_like(pp, 1.1754944e-38)); ps.append(pp)                             # smallest normal
+    # every k / 255 boundary of the byte for a few p: g just below, at and above p * k / 255
+    k = torch.arange(0, 256, dtype=torch.float64)
+    for pv in (1.0, 3.0, 1000.0, 0.7, 12345.678, 2.0 ** 20 + 1):
+        base = torch.tensor(pv, dtype=torch.float32)
+        b = (base.double() * k / 255.0).float()
+        for gq in (b, torch.nextafter(b, torch.zeros_like(b)), torch.nextafter(b, torch.full_like(b, 1e30))):
+            gs.append(gq.minimum(base.expand_as(gq))); ps.append(base.expand_as(gq).clone())
+    bad_q, bad_b, bad_2, seen = run(torch.cat(gs), torch.cat(ps))
+    assert seen > 5000 and (bad_q, bad_b, bad_2) == (0, 0, 0)
+    # random pairs: exponent of p uniform over the guard range, random mantissa, g = p * u
+    gen = torch.Generator(device=cuda_device).manual_seed(1234)
+    total = 0
+    for _ in range(5):
+        n = 20_000_000
+        e = torch.randint(68, 187, (n,), generator=gen, device=cuda_device, dtype=torch.int32)
+        m = torch.randint(0, 1 << 23, (n,), generator=gen, device=cuda_device, dtype=torch.int32)
+        p = ((e << 23) | m).view(torch.float32)
+        u = torch.rand(n, generator=gen, device=cuda_device, dtype=torch.float64)
+        g = (p.double() * u).float().minimum(p)
+        bad_q, bad_b, bad_2, seen = run(g, p)
+        assert (bad_q, bad_b, bad_2) == (0, 0, 0), (bad_q, bad_b, bad_2, seen)
+        total += seen
+    assert total > 90_000_000

@@ -120,6 +120,12 @@ int msl_lesion_slices(const void* gt, int dtype, int nvol, int X, int Y, int Z,
     return launch_lesion_flags(gt, dtype, nvol, X, Y, Z, any_ax, any_co, any_sa, (cudaStream_t)stream);
 }
 
+int msl_selftest_norm_division(const float* g, const float* p, size_t n, unsigned long long* out4, msl_stream_t stream_) {
+    if ((!g || !p) && n) { set_error("msl_selftest_norm_division: NULL operands"); return MSL_ERR_ARG; }
+    if (!out4) { set_error("msl_selftest_norm_division: NULL result"); return MSL_ERR_ARG; }
+    return launch_selftest_norm_division(g, p, n, out4, reinterpret_cast<cudaStream_t>(stream_));
+}
+
 int msl_slice_ranges(const float* vol, int nvol, int X, int Y, int Z, float* ranges, msl_stream_t stream_) {
     MSL_REQUIRE(vol && ranges, "NULL pointer");
     MSL_REQUIRE(nvol > 0 && X > 0 && Y > 0 && Z > 0, "non-positive size");

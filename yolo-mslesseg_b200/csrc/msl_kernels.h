@@ -80,6 +80,7 @@ int launch_enhance_slices(EnhParams p, int dtype, int nslices, cudaStream_t stre
 // stats: [nvol][Z + Y + X][2] = {min key, max key}; must be pre-initialised by init_stats.
 int launch_init_stats(unsigned* stats, size_t nslices_total, cudaStream_t stream);
 int launch_plane_stats_f32(const float* vol, int nvol, int X, int Y, int Z, unsigned* stats, cudaStream_t stream);
+int launch_selftest_norm_division(const float* g, const float* p, size_t n, unsigned long long* out, cudaStream_t stream);
 int launch_stats_keys_to_float(unsigned* stats, size_t n, cudaStream_t stream);    // order-preserving keys -> float bits, in place
 
 // E0: any(voxel > 0) per slice for the three planes.
