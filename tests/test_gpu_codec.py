@@ -238,6 +238,13 @@ def test_nifti_gz_round_trip_on_device(ops, codec, cuda_device, tmp_path):
     # values a uint8 volume cannot hold are refused
     with pytest.raises(codec.CodecError):
         codec.nifti_load_device(p1, cuda_device, torch.uint8)
+    # dataset preparation: a foreign single-member file is rewritten with the member index, its decoded bytes unchanged
+    before = gzip.decompress(p1.read_bytes())
+    assert codec.gzip_member_table(p1.read_bytes()) is None
+    assert codec.reindex_gz(p1) is True and codec.reindex_gz(p1) is False
+    assert codec.gzip_member_table(p1.read_bytes()) is not None and gzip.decompress(p1.read_bytes()) == before
+    vol3, _, _ = codec.nifti_load_device(p1, cuda_device, torch.float32)
+    assert torch.equal(vol3, vol)
 
 
 def test_deflate_files_prefix_expand_and_index(ops, codec, cuda_device):

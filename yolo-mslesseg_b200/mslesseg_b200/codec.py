@@ -388,3 +388,48 @@ def nifti_save_device(vol_zyx: torch.Tensor, affine, path) -> int:
     with open(path, "wb") as f:
         f.write(blob)
     return len(blob)
+
+
+# ------------------------------------------------------------------------------------------------ dataset preparation
+def reindex_gz(path, dest=None, device=None) -> bool:
+    """Rewrites a .gz file from another writer (one member, one long deflate stream: a single warp's serial work, about a
+    second per MSLesSeg volume) as the member-indexed file this package writes (16 KB of raw bytes per member + the index
+    member: one warp per member, a fraction of a millisecond per volume).  Both the decode and the encode run on the GPU; the
+    decoded bytes are unchanged, so nibabel / gzip read the new file exactly like the old one.  Returns False when the file
+    already carries the index.  Meant to be run once over a dataset (`python -m mslesseg_b200.codec reindex <files>`)."""
+    path = Path(path)
+    blob = path.read_bytes()
+    if gzip_member_table(blob) is not None:
+        return False
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    members = gzip_members(blob)                  # walks the members when they carry their size, else None
+    if members is None:
+        isize = int.from_bytes(blob[-4:], "little")      # ISIZE of the last member = the file for a single-member file < 4 GB
+        dst, _ = inflate([blob], [isize], "gzip", device)
+        raw = dst[:isize]
+    else:
+        pieces = [blob[o:o + m] for o, m, _ in members]
+        dst, off = inflate(pieces, [r for _, _, r in members], "gzip", device)
+        raw = torch.cat([dst[int(off[i]):int(off[i]) + members[i][2]] for i in range(len(members))])
+    elem = 1
+    if raw.numel() >= 352 and int.from_bytes(raw[:4].cpu().numpy().tobytes(), "little") == 348:      # NIfTI-1: bitpix at byte 72
+        elem = max(1, min(4, int.from_bytes(raw[72:74].cpu().numpy().tobytes(), "little") // 8))
+    ps = ops.deflate_chunks(raw.contiguous(), chunk_len=CHUNK, container="gzip", dist2=elem)
+    out = nifti_gz_bytes(ps)
+    dest = Path(dest) if dest is not None else path
+    tmp = dest.with_name(dest.name + ".tmp")
+    tmp.write_bytes(out)
+    tmp.replace(dest)
+    return True
+
+
+if __name__ == "__main__":
+    import sys
+    if len(sys.argv) < 3 or sys.argv[1] != "reindex":
+        raise SystemExit("usage: python -m mslesseg_b200.codec reindex <file.nii.gz | directory> ...")
+    todo = []
+    for a in sys.argv[2:]:
+        todo += sorted(Path(a).rglob("*.nii.gz")) if Path(a).is_dir() else [Path(a)]
+    for f in todo:
+        print(("reindexed " if reindex_gz(f) else "kept      ") + str(f))
