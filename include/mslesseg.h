@@ -145,6 +145,20 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z,
                         uint8_t* const* outs, const uint8_t* tables,
                         void* ws, size_t ws_bytes, msl_stream_t stream);
 
+/* ---- E3-E6 on a staged stack of normalised slices ----------------------------------------------
+ * The per-slice stage of msl_enhance_volumes on its own: `nslices` uint8 slices that already went through E1 (e.g.
+ * msl_enhance_slices with MSL_MEJORA_NONE and layout MSL_OUT_P into a buffer whose slice pitch is a multiple of 16 bytes),
+ * PNG orientation [cols][rows], -> any of HE / CLAHE / GC / LT (utils/mejora_imagen.py:52-184), densely packed
+ * [nslices][cols][rows], same orientation.  rows x cols = the slice orientation of the plane (what clahe's tile grid is laid
+ * over).  Same bytes as msl_enhance_slices produces slice by slice, at the speed of the whole-volume kernel; this is how
+ * mslesseg_b200.ops.enhance_slices runs long slice lists (Paciente.cortes_con_lesion_* of a whole cohort).
+ * ws: msl_enhance_stack_workspace_bytes(rows, cols) bytes, 16-byte aligned (only read when out_clahe is given).
+ * MSL_ERR_UNSUPPORTED when the geometry is outside the dense kernel's range. */
+size_t msl_enhance_stack_workspace_bytes(int rows, int cols);
+int msl_enhance_stack(const uint8_t* stack_p, size_t slice_pitch_bytes, int nslices, int rows, int cols,
+                      uint8_t* out_he, uint8_t* out_clahe, uint8_t* out_gc, uint8_t* out_lt,
+                      const uint8_t* tables, void* ws, size_t ws_bytes, msl_stream_t stream);
+
 /* ---- E8 container: PNG files around the imsave pixels (encode side) ---------------
  * Replaces the per-slice PNG encode behind plt.imsave (scripts/extraer_dataset.py:192,197).  pixels: uint8
  * [n][H][W][channels], channels 4 (RGBA, colour type 6 - what imsave writes) or 1 (gray, colour type 0).

@@ -653,3 +653,42 @@ def test_norm_division_selftest(ops, torch_mod, cuda_device):
         assert (bad_q, bad_b, bad_2) == (0, 0, 0), (bad_q, bad_b, bad_2, seen)
         total += seen
     assert total > 90_000_000
+
+
+def test_long_slice_lists_take_the_dense_kernel(ops, torch_mod, cuda_device, monkeypatch):
+    """ops.enhance_slices stages long lists (E1 per slice, PNG orientation) and runs the whole-volume kernel over the stack
+    (msl_enhance_stack): same bytes as the per-slice kernel, for every enhancement / plane and duplicates."""
+    torch = torch_mod
+    from mslesseg_b200 import synthetic as S
+    rng = np.random.default_rng(5)
+    pats = [S.make_patient(1 + b, config_id=4, num_cortes=8) for b in range(2)]
+    vol = torch.from_numpy(np.stack([p.flair for p in pats])).to(cuda_device)
+    volu8 = torch.from_numpy(np.stack([p.gt for p in pats]) * 200).to(cuda_device)
+    for plano, n_p in (("axial", 182), ("coronal", 218), ("sagital", 182)):
+        vs = rng.integers(0, 2, 150).tolist()
+        ix = rng.integers(0, n_p, 150).tolist()
+        ix[3] = ix[4]; vs[3] = vs[4]                                # a duplicate
+        for mej in ("HE", "CLAHE", "GC", "LT"):
+            for v in (vol, volu8):
+                monkeypatch.setattr(ops, "_STACK_MIN_SLICES", 1 << 30)
+                want = ops.enhance_slices(v, mej, plano, vs, ix, layout="P")
+                monkeypatch.setattr(ops, "_STACK_MIN_SLICES", 64)
+                before = _lib_launches("enhance_dense")
+                got = ops.enhance_slices(v, mej, plano, vs, ix, layout="P")
+                assert _lib_launches("enhance_dense") == before + (1 if v is vol else 0)      # uint8 volumes keep the slice kernel
+                assert torch.equal(got, want), (plano, mej, str(v.dtype))
+    # the colour LUTs of CLAHE's channel-wise path, and whole volumes without an index list
+    monkeypatch.setattr(ops, "_STACK_MIN_SLICES", 1 << 30)
+    want = ops.enhance_slices(vol, "CLAHE", "axial", layout="P", lut_out="R")
+    monkeypatch.setattr(ops, "_STACK_MIN_SLICES", 64)
+    assert torch.equal(ops.enhance_slices(vol, "CLAHE", "axial", layout="P", lut_out="R"), want)
+
+
+def _lib_launches(kind):
+    import ctypes
+    from mslesseg_b200 import _lib
+    lib = _lib.load()
+    n = lib.msl_kernel_kinds()
+    per = (ctypes.c_ulonglong * n)()
+    lib.msl_kernel_launches(per)
+    return {lib.msl_kernel_name(k).decode(): int(per[k]) for k in range(n)}.get(kind, 0)

@@ -297,6 +297,31 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z, uint8_t
     return MSL_OK;
 }
 
+size_t msl_enhance_stack_workspace_bytes(int rows, int cols) { return dense_tabs_bytes(rows, cols); }
+
+int msl_enhance_stack(const uint8_t* stack_p, size_t slice_pitch_bytes, int nslices, int rows, int cols,
+                      uint8_t* out_he, uint8_t* out_clahe, uint8_t* out_gc, uint8_t* out_lt,
+                      const uint8_t* tables, void* ws, size_t ws_bytes, msl_stream_t stream) {
+    MSL_REQUIRE(stack_p && tables, "NULL pointer");
+    MSL_REQUIRE(nslices >= 0 && rows > 0 && cols > 0, "non-positive size");
+    MSL_REQUIRE(out_he || out_clahe || out_gc || out_lt, "no output wanted");
+    MSL_REQUIRE(slice_pitch_bytes >= (size_t)rows * cols && (slice_pitch_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(stack_p) & 15) == 0,
+                "the staged stack needs a 16-byte aligned base and a slice pitch that is a multiple of 16 bytes");
+    if (nslices == 0) return MSL_OK;
+    if (!dense_supported(rows, cols, out_clahe != nullptr)) {
+        set_error("msl_enhance_stack: %d x %d slices are outside the dense kernel's range (use msl_enhance_images)", rows, cols);
+        return MSL_ERR_UNSUPPORTED;
+    }
+    EnhParams p;
+    memset(&p, 0, sizeof(p));
+    clahe_geometry(rows, cols, p);
+    DensePlane q;
+    q.U = stack_p; q.u_pitch = slice_pitch_bytes; q.nslices = nslices; q.rows = rows; q.cols = cols;
+    q.out_he = out_he; q.out_clahe = out_clahe; q.out_gc = out_gc; q.out_lt = out_lt;
+    q.th = p.cl_th; q.tw = p.cl_tw; q.clip = p.cl_clip; q.lut_scale = p.cl_lut_scale;
+    return launch_enhance_dense_multi(&q, 1, tables, ws, ws_bytes, (cudaStream_t)stream);
+}
+
 size_t msl_png_bytes(int H, int W, int channels) {
     if (H <= 0 || W <= 0 || (channels != 1 && channels != 4)) return 0;
     return png_file_bytes(H, W, channels);
