@@ -155,6 +155,12 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z,
  * ws: msl_enhance_stack_workspace_bytes(rows, cols) bytes, 16-byte aligned (only read when out_clahe is given).
  * MSL_ERR_UNSUPPORTED when the geometry is outside the dense kernel's range. */
 size_t msl_enhance_stack_workspace_bytes(int rows, int cols);
+/* E1 + E2 for a slice list, the front half of that route: slice s = (vol_of_slice[s], idx_of_slice[s]) of plane `plano` of
+ * the float32 volumes (NULL lists: every slice of every volume) is normalised like normalizar_a_uint8 (utils/utils.py:396-406)
+ * and written in PNG orientation to out + s * slice_pitch_bytes.  Pairs outside the volumes are skipped.
+ * MSL_ERR_UNSUPPORTED for odd slice rows (use msl_enhance_slices with MSL_MEJORA_NONE). */
+int msl_stage_slices(const float* vol, int nvol, int X, int Y, int Z, int plano, const int32_t* vol_of_slice,
+                     const int32_t* idx_of_slice, int nslices, uint8_t* out, size_t slice_pitch_bytes, msl_stream_t stream);
 int msl_enhance_stack(const uint8_t* stack_p, size_t slice_pitch_bytes, int nslices, int rows, int cols,
                       uint8_t* out_he, uint8_t* out_clahe, uint8_t* out_gc, uint8_t* out_lt,
                       const uint8_t* tables, void* ws, size_t ws_bytes, msl_stream_t stream);

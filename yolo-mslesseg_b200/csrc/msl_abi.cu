@@ -297,6 +297,20 @@ int msl_enhance_volumes(const float* vol, int nvol, int X, int Y, int Z, uint8_t
     return MSL_OK;
 }
 
+int msl_stage_slices(const float* vol, int nvol, int X, int Y, int Z, int plano, const int32_t* vol_of_slice,
+                     const int32_t* idx_of_slice, int nslices, uint8_t* out, size_t slice_pitch_bytes, msl_stream_t stream) {
+    MSL_REQUIRE(vol && out, "NULL pointer");
+    MSL_REQUIRE(nvol > 0 && X > 0 && Y > 0 && Z > 0 && nslices >= 0, "non-positive size");
+    MSL_REQUIRE(plano >= MSL_AXIAL && plano <= MSL_SAGITAL, "Plano %d no válido.", plano);
+    MSL_REQUIRE((vol_of_slice == nullptr) == (idx_of_slice == nullptr), "vol_of_slice and idx_of_slice must both be given or both be NULL");
+    const int n_plane = n_plane_of(plano, X, Y, Z);
+    const long long npx = (long long)X * Y * Z / n_plane;
+    if (!vol_of_slice)
+        MSL_REQUIRE((long long)nslices == (long long)nvol * n_plane, "dense mode needs nslices == nvol * n_plane (%lld), got %d", (long long)nvol * n_plane, nslices);
+    MSL_REQUIRE(slice_pitch_bytes >= (size_t)npx, "slice pitch smaller than a slice");
+    return launch_stage_slices(vol, nvol, X, Y, Z, plano, vol_of_slice, idx_of_slice, nslices, out, slice_pitch_bytes, (cudaStream_t)stream);
+}
+
 size_t msl_enhance_stack_workspace_bytes(int rows, int cols) { return dense_tabs_bytes(rows, cols); }
 
 int msl_enhance_stack(const uint8_t* stack_p, size_t slice_pitch_bytes, int nslices, int rows, int cols,

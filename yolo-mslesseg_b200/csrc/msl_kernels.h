@@ -35,7 +35,8 @@ enum KernelKind {
     K_NIFTI_CONVERT = 31,
     K_CHECKSUM = 32,
     K_CONTOURS = 33,
-    K_NKIND = 34
+    K_STAGE_SLICES = 34,
+    K_NKIND = 35
 };
 
 // RAII: counts the launch and, when profiling is enabled, brackets it with CUDA events on `stream`.
@@ -80,6 +81,8 @@ int launch_enhance_slices(EnhParams p, int dtype, int nslices, cudaStream_t stre
 // stats: [nvol][Z + Y + X][2] = {min key, max key}; must be pre-initialised by init_stats.
 int launch_init_stats(unsigned* stats, size_t nslices_total, cudaStream_t stream);
 int launch_plane_stats_f32(const float* vol, int nvol, int X, int Y, int Z, unsigned* stats, cudaStream_t stream);
+int launch_stage_slices(const float* vol, int nvol, int X, int Y, int Z, int plano, const int32_t* vol_of_slice, const int32_t* idx_of_slice,
+                        int nslices, uint8_t* out, size_t out_pitch, cudaStream_t stream);
 int launch_selftest_norm_division(const float* g, const float* p, size_t n, unsigned long long* out, cudaStream_t stream);
 int launch_stats_keys_to_float(unsigned* stats, size_t n, cudaStream_t stream);    // order-preserving keys -> float bits, in place
 

@@ -23,7 +23,7 @@ const char* const kNames[K_NKIND] = {
     "init_stats", "plane_stats_f32", "lesion_flags", "norm_scatter",
     "recon_fill", "recon_slot_map", "recon_gather", "consensus_eval", "confusion_counts", "enhance_dense",
     "combine_predictions", "slice_counts", "bgr_to_gray", "png_pack", "nonzero_flags", "enhance_dense_tables",
-    "deflate", "deflate_scan", "deflate_pack", "inflate", "png_unfilter", "nifti_convert", "checksum", "contours",
+    "deflate", "deflate_scan", "deflate_pack", "inflate", "png_unfilter", "nifti_convert", "checksum", "contours", "stage_slices",
 };
 }  // namespace
 

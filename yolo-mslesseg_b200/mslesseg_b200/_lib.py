@@ -68,6 +68,8 @@ _SIGNATURES = {
     "msl_kernel_launches": (C.c_ulonglong, [C.POINTER(C.c_ulonglong)]),
     "msl_profile_enable": (C.c_int, [_i]),
     "msl_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
+    "msl_stage_slices": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t,
+                                   C.c_void_p]),
     "msl_enhance_stack_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "msl_enhance_stack": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

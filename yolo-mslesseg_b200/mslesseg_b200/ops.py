@@ -191,9 +191,12 @@ def enhance_slices(vol: torch.Tensor, mejora: Optional[str], plano: str, vol_of_
         # stack - the same bytes as the per-slice kernel below, at a third of its time
         upitch = (rows * cols + 15) & ~15
         stage = torch.empty((ns, upitch), dtype=torch.uint8, device=vol.device)
-        L.check(lib.msl_enhance_slices(
-            _ptr(vol), _dtype_id(vol, "vol"), nvol, X, Y, Z, L.MEJORA_NONE, L.PLANO_ID[plano],
-            _ptr(vs), _ptr(ix), ns, _ptr(stage), upitch, _LAYOUT_ID["P"], _ptr(tabs), _stream()))
+        rc = lib.msl_stage_slices(_ptr(vol), nvol, X, Y, Z, L.PLANO_ID[plano], _ptr(vs), _ptr(ix), ns, _ptr(stage), upitch, _stream())
+        if rc == L.ERR_UNSUPPORTED:
+            rc = lib.msl_enhance_slices(
+                _ptr(vol), _dtype_id(vol, "vol"), nvol, X, Y, Z, L.MEJORA_NONE, L.PLANO_ID[plano],
+                _ptr(vs), _ptr(ix), ns, _ptr(stage), upitch, _LAYOUT_ID["P"], _ptr(tabs), _stream())
+        L.check(rc)
         ws = torch.empty(int(lib.msl_enhance_stack_workspace_bytes(rows, cols)) + 16, dtype=torch.uint8, device=vol.device)
         dst = [_ptr(out) if mejora == m else None for m in ("HE", "CLAHE", "GC", "LT")]
         rc = lib.msl_enhance_stack(_ptr(stage), upitch, ns, rows, cols, *dst, _ptr(tabs), _ptr(ws), ws.numel(), _stream())
