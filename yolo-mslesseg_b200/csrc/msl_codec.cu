@@ -9,13 +9,13 @@
 //   (skull-stripped background, masks, padding), so the stream is built from two kinds of blocks decided per WARP:
 //   a tile of 4 KB is cut into 256 segments of 16 bytes, one per thread, held in four registers; a byte-SIMD compare gives
 //   each thread the mask x[i] == x[i - d] (d = 1: repeated bytes, 4: repeated RGBA pixels / float32 voxels); a ballot tells
-//   the warp which of its 32 segments are entirely inside a run.  Every maximal group of neighbouring run segments becomes
-//   ONE fixed-Huffman block of one or two matches (looked up in a 32-entry table built per launch); every group of other
-//   segments becomes ONE stored block (raw bytes, byte aligned).  A warp's output is therefore whole bytes (a fixed block is
-//   realigned by the header of the stored block behind it, an empty one at the end of the warp), sizes are known from the
-//   ballot alone, a warp scan + block scan places every lane, headers are written by the lanes that start a block and every
+//   the warp which of its 32 segments are entirely inside a run.  Every maximal group of neighbouring run segments of a tile
+//   becomes ONE fixed-Huffman block of 258-byte matches (at most sixteen of them + end of block); every group of other
+//   segments becomes ONE stored block (raw bytes, byte aligned).  Every block is therefore whole bytes (a fixed block is
+//   realigned by the header of the stored block behind it, an empty one at the end of the tile), sizes are known from the
+//   ballots alone, a warp scan + block scan places every lane, headers are written by the lanes that start a block and every
 //   literal lane copies its own 16 bytes.  No literal is ever Huffman-coded - neither here nor in the decoder, which meets
-//   a handful of symbols per 512 bytes.  The next tile is loaded while this one is encoded (image mode: aligned words,
+//   a handful of symbols per kilobyte.  The next tile is loaded while this one is encoded (image mode: aligned words,
 //   funnel-shifted, the filter byte shifted in), two staging buffers alternate so that a tile costs three barriers;
 //   16-byte flushes, the carry to the next tile, Adler-32 (dp4a) / CRC-32 (slicing by four from registers + one GF(2)
 //   multiplication per thread) of the raw bytes and the container header / trailer are handled by the same CTA.
@@ -133,19 +133,28 @@ __host__ __device__ inline int match_bits(int len, int d, uint32_t& pat) {
     return n + (int)eb + 5;
 }
 
-// A run of 16 * (k + 1) bytes (k = 0..31: whole segments of one warp) as ONE fixed-Huffman block: header (BFINAL 0, BTYPE 01),
-// one or two matches (258 + the rest: the rest of a multiple of 16 is never 1 or 2), end of block.  Bits 0..47 hold the
-// block LSB first, bits 48..55 its length in bits (at most 3 + 13 + 18 + 7).
-__host__ __device__ inline unsigned long long run_block(int k, int d) {
-    const int bytes = kSeg * (k + 1);
-    unsigned long long acc = 2u;
-    int n = 3;
+// A run of `bytes` bytes (whole segments of one tile, up to 4 KB) as ONE fixed-Huffman block: header (BFINAL 0, BTYPE 01),
+// matches of 258 bytes + the rest (a rest of 1 or 2 bytes is not a match: the last two matches then share 258 + rest bytes),
+// end of block.  Returns the bits; W::put(pattern, nbits) receives them in order (a counting writer just sizes the block).
+struct BitCounter { __host__ __device__ void put(uint32_t, int) {} };
+struct ByteWriter {                              // (host side: the all-zero chunk template)
+    uint8_t* b; unsigned long long bit;
+    __host__ __device__ void put(uint32_t v, int n) { for (int i = 0; i < n; ++i, ++bit) if ((v >> i) & 1u) b[bit >> 3] |= (uint8_t)(1u << (bit & 7)); }
+};
+template <class W>
+__host__ __device__ inline int emit_run(W& w, int bytes, int d) {
+    int q = bytes / 258, r = bytes - 258 * q, tail2 = 0;
+    if (r > 0 && r < 3) { q -= 1; tail2 = 3; r = 258 + r - 3; }
     uint32_t pat;
-    if (bytes >= 258 + 3) { const int m = match_bits(258, d, pat); acc |= (unsigned long long)pat << n; n += m; }
-    const int rest = bytes >= 258 + 3 ? bytes - 258 : bytes;
-    { const int m = match_bits(rest, d, pat); acc |= (unsigned long long)pat << n; n += m; }
-    n += 7;
-    return acc | ((unsigned long long)n << 48);
+    int n = 3;
+    w.put(2u, 3);
+    const int m258 = match_bits(258, d, pat);
+    for (int i = 0; i < q; ++i) w.put(pat, m258);
+    n += q * m258;
+    if (r) { const int m = match_bits(r, d, pat); w.put(pat, m); n += m; }
+    if (tail2) { const int m = match_bits(tail2, d, pat); w.put(pat, m); n += m; }
+    w.put(0u, 7);
+    return n + 7;
 }
 
 // Tile bytes in shared memory: logical index i (>= -64) lives at i + 4 * ((i + 64) / 64): every thread's 64-byte segment
@@ -192,8 +201,8 @@ __device__ __forceinline__ SegMasks seg_masks(const uint8_t* X, int beg, int end
 }
 
 // ---- a tile's 256 segments as blocks, every lane working for itself
-// A maximal group of literal segments becomes ONE stored block (up to the whole 4 KB tile, across warps); run segments become
-// one fixed-Huffman block per warp and group.  A stored block ends on a byte boundary, so every fixed block STARTS on one (at
+// A maximal group of literal segments becomes ONE stored block, a maximal group of run segments ONE fixed-Huffman block (either
+// may span the whole 4 KB tile, across warps).  A stored block ends on a byte boundary, so every fixed block STARTS on one (at
 // the tile's first byte, behind a stored block, or behind the empty stored block that closes the previous fixed block).  That
 // makes every size local: the lane that starts a fixed block emits the block and the header of the stored block behind it (an
 // empty one when another fixed block or the end of the tile follows) - whole bytes; a literal lane accounts for its own bytes,
@@ -206,6 +215,19 @@ struct LanePlan {
     int hbits;        // bits of the fixed block (header + matches + end of block)
     int size;         // bytes this lane contributes to the tile's output
 };
+
+// run segments in a row from segment e of the tile on
+__device__ __forceinline__ int run_group_segments(const unsigned* tile_runs, int e, int nseg) {
+    int s = e;
+    while (s < nseg) {
+        const int b = s & 31;
+        const unsigned x = tile_runs[s >> 5] >> b;
+        const int ones = min(x == (0xffffffffu >> b) ? 32 - b : __ffs((int)~x) - 1, nseg - s);
+        s += ones;
+        if (ones < 32 - b) break;
+    }
+    return s - e;
+}
 
 // bytes of the literal group that starts at segment e of the tile (0 when that segment is a run or behind the end)
 __device__ __forceinline__ int literal_group_bytes(const unsigned* tile_runs, int e, int nseg, unsigned tn) {
@@ -220,8 +242,7 @@ __device__ __forceinline__ int literal_group_bytes(const unsigned* tile_runs, in
     return s > e ? min(kSeg * (s - e), (int)tn - kSeg * e) : 0;
 }
 
-__device__ __forceinline__ LanePlan lane_plan(const unsigned* tile_runs, int warp, int lane, int nseg, unsigned tn, int len,
-                                              const unsigned long long* run_tab) {
+__device__ __forceinline__ LanePlan lane_plan(const unsigned* tile_runs, int warp, int lane, int nseg, unsigned tn, int len, int d) {
     LanePlan p;
     p.start = false; p.run = false; p.hdr = false; p.bytes = 0; p.next_bytes = 0; p.hbits = 0; p.size = 0;
     const int seg = warp * 32 + lane;
@@ -229,13 +250,14 @@ __device__ __forceinline__ LanePlan lane_plan(const unsigned* tile_runs, int war
     const unsigned my = tile_runs[warp];
     p.run = (my >> lane) & 1u;
     if (p.run) {
-        p.start = lane == 0 || !((my >> (lane - 1)) & 1u);
+        const bool prev_run = seg > 0 && (((lane ? my >> (lane - 1) : tile_runs[warp - 1] >> 31)) & 1u);
+        p.start = !prev_run;
         if (!p.start) return p;
-        const unsigned x = my >> lane;                                 // run segments from this lane on
-        const int nl = min(x == (0xffffffffu >> lane) ? 32 - lane : __ffs((int)~x) - 1, nseg - seg);
+        const int nl = run_group_segments(tile_runs, seg, nseg);       // (may reach into the following warps)
         p.bytes = kSeg * nl;
         p.next_bytes = literal_group_bytes(tile_runs, seg + nl, nseg, tn);
-        p.hbits = (int)(run_tab[nl - 1] >> 48);
+        BitCounter none;
+        p.hbits = emit_run(none, p.bytes, d);
         p.size = ((p.hbits + 3 + 7) >> 3) + 4;
     } else {
         p.hdr = seg == 0;
@@ -258,19 +280,33 @@ __device__ __forceinline__ void stage_bytes(uint32_t* Y32, unsigned at, unsigned
 }
 
 // emission: at = this lane's place in the staging area (the tile's first byte + the exclusive prefix of the sizes)
-__device__ __forceinline__ void lane_emit(const LanePlan& p, const SegMasks& m, const unsigned long long* run_tab, uint8_t* Ys, unsigned at) {
+// bits into the zeroed staging area from byte `at` on (words are OR-ed in: neighbours may share the first and the last one)
+struct StageWriter {
+    uint32_t* y;
+    unsigned word;
+    unsigned long long acc;
+    int nacc;
+    __device__ __forceinline__ void init(uint32_t* y_, unsigned at) { y = y_; word = at >> 2; nacc = 8 * (int)(at & 3u); acc = 0; }
+    __device__ __forceinline__ void put(uint32_t v, int n) {
+        acc |= (unsigned long long)v << nacc;
+        nacc += n;
+        if (nacc >= 32) { if ((uint32_t)acc) atomicOr(&y[word], (uint32_t)acc); ++word; acc >>= 32; nacc -= 32; }
+    }
+    __device__ __forceinline__ void finish() { if (nacc > 0 && (uint32_t)acc) atomicOr(&y[word], (uint32_t)acc); }
+};
+
+__device__ __forceinline__ void lane_emit(const LanePlan& p, const SegMasks& m, int d, uint8_t* Ys, unsigned at) {
     uint32_t* Y32 = reinterpret_cast<uint32_t*>(Ys);
     if (p.start) {
         if (p.run) {
             // the fixed block, the header of the stored block behind it (three zero bits + padding), LEN / NLEN
-            const unsigned long long blk = run_tab[p.bytes / kSeg - 1] & 0xffffffffffffull;
-            const int nb1 = (p.hbits + 3 + 7) >> 3;                // <= 7 bytes
+            StageWriter w;
+            w.init(Y32, at);
+            emit_run(w, p.bytes, d);
+            w.finish();
+            const unsigned nb1 = (unsigned)(p.hbits + 3 + 7) >> 3;
             const uint32_t len = (uint32_t)p.next_bytes | ((~(uint32_t)p.next_bytes & 0xffffu) << 16);
-            unsigned long long lo = blk;
-            uint32_t hi = 0;
-            lo |= (unsigned long long)len << (8 * nb1);
-            if (nb1 > 4) hi = len >> (8 * (8 - nb1));
-            stage_bytes(Y32, at, lo, hi);
+            stage_bytes(Y32, at + nb1, (unsigned long long)len, 0u);
         } else {
             const uint32_t len = (uint32_t)p.bytes | ((~(uint32_t)p.bytes & 0xffffu) << 16);
             stage_bytes(Y32, at, (unsigned long long)len << 8, 0u);
@@ -402,7 +438,6 @@ __global__ void __launch_bounds__(kZThreads, 4) deflate_kernel(const ZArgs a) {
     __shared__ __align__(16) uint8_t Ys2[2][kYBytes + 16];
     __shared__ uint32_t crc_table[4][256];            // slicing by four: table k = a byte followed by k zero bytes
     __shared__ uint32_t crc_part[kZThreads / 32];
-    __shared__ unsigned long long run_tab[32];
     __shared__ unsigned tile_runs[kZThreads / 32];     // bit l of word w: segment 32 w + l of the tile lies inside a run
     __shared__ int scan_w[kZThreads / 32];
     __shared__ unsigned long long red_a[kZThreads / 32], red_b[kZThreads / 32];
@@ -433,7 +468,6 @@ __global__ void __launch_bounds__(kZThreads, 4) deflate_kernel(const ZArgs a) {
 
     const int dist = a.dist2 ? a.dist2 : 1;
     if (want_crc) crc_tables(crc_table, tid);
-    if (tid < 32) run_tab[tid] = run_block(tid, dist);
     for (int q0_ = 0; q0_ < ((kYBytes + 16) / 4); q0_ += kZThreads) if (const int q = q0_ + (int)tid; q < ((kYBytes + 16) / 4)) Y32[q] = 0;
     if (tid < kLook / 4) reinterpret_cast<uint32_t*>(Xs)[tid] = 0;
     block_sync();
@@ -539,7 +573,7 @@ __global__ void __launch_bounds__(kZThreads, 4) deflate_kernel(const ZArgs a) {
             }
         }
         // ---- blocks: sizes from the run masks of the tile, a scan over lanes and warps, emission
-        const LanePlan plan = lane_plan(tile_runs, warp, lane, (int)((tn + kSeg - 1) / kSeg), tn, m.len, run_tab);
+        const LanePlan plan = lane_plan(tile_runs, warp, lane, (int)((tn + kSeg - 1) / kSeg), tn, m.len, dist);
         const int lincl = warp_incl_scan(plan.size, lane);
         if (lane == 31) scan_w[warp] = lincl;
         block_sync();
@@ -552,7 +586,7 @@ __global__ void __launch_bounds__(kZThreads, 4) deflate_kernel(const ZArgs a) {
             for (int w = 0; w < kZThreads / 32; ++w) t ^= crc_part[w];
             crc_run = t;
         }
-        lane_emit(plan, m, run_tab, Ys, (bit0 >> 3) + (unsigned)(wbase + lincl - plan.size));
+        lane_emit(plan, m, dist, Ys, (bit0 >> 3) + (unsigned)(wbase + lincl - plan.size));
         total *= 8;
         block_sync();
         const unsigned nbits = bit0 + (unsigned)total;
@@ -795,19 +829,17 @@ void zero_chunk_stream(int container, int d, unsigned n, uint32_t meta[4], uint8
         memcpy(b, h, 16); p = 24;
     }
     auto put_run = [&](int nl) {               // a run of nl segments: fixed block, empty stored block behind it
-        const unsigned long long blk = run_block(nl - 1, d);
-        const int hbits = (int)(blk >> 48), nb1 = (hbits + 3 + 7) >> 3;
-        for (int i = 0; i < nb1; ++i) b[p++] = (uint8_t)((blk & 0xffffffffffffull) >> (8 * i));
+        ByteWriter w{b, 8ull * p};
+        const int hbits = emit_run(w, kSeg * nl, d);
+        p += (unsigned)(hbits + 3 + 7) >> 3;
         b[p++] = 0; b[p++] = 0; b[p++] = 0xff; b[p++] = 0xff;
     };
     for (unsigned t = 0; t < n / kTile; ++t) {
-        for (int w = 0; w < kZThreads / 32; ++w) {
-            if (t == 0 && w == 0) {
-                b[p++] = 0; b[p++] = kSeg; b[p++] = 0; b[p++] = (uint8_t)~kSeg; b[p++] = 0xff;
-                p += kSeg;                      // the sixteen zero bytes themselves
-                put_run(31);
-            } else put_run(32);
-        }
+        if (t == 0) {
+            b[p++] = 0; b[p++] = kSeg; b[p++] = 0; b[p++] = (uint8_t)~kSeg; b[p++] = 0xff;
+            p += kSeg;                          // the sixteen zero bytes themselves
+            put_run(kZThreads - 1);
+        } else put_run(kZThreads);
     }
     b[p++] = 1; b[p++] = 0; b[p++] = 0; b[p++] = 0xff; b[p++] = 0xff;
     uint32_t chk = 0;
