@@ -70,6 +70,29 @@ def test_argument_errors_of_the_widened_entry_points_without_gpu():
     assert lib.msl_bgr_to_gray(None, 0, None, None) == 0
 
 
+def test_argument_errors_of_the_round2_entry_points_without_gpu():
+    lib = _lib.load()
+    P, Q = ctypes.c_void_p(4096), ctypes.c_void_p(4100)
+    # staged-stack route: pitch / alignment / outputs are checked before any CUDA call
+    assert lib.msl_enhance_stack_workspace_bytes(182, 218) > 0 and lib.msl_enhance_stack_workspace_bytes(182, 218) % 16 == 0
+    assert lib.msl_enhance_stack(P, 39680, 4, 182, 218, None, None, None, None, P, P, 1 << 20, None) == _lib.ERR_ARG
+    assert b"no output" in lib.msl_last_error()
+    assert lib.msl_enhance_stack(P, 39676, 4, 182, 218, P, None, None, None, P, P, 1 << 20, None) == _lib.ERR_ARG
+    assert b"pitch" in lib.msl_last_error()
+    assert lib.msl_enhance_stack(Q, 39680, 4, 182, 218, P, None, None, None, P, P, 1 << 20, None) == _lib.ERR_ARG
+    assert lib.msl_enhance_stack(P, 39680, 0, 182, 218, P, None, None, None, P, P, 1 << 20, None) == 0          # nothing to do
+    assert lib.msl_enhance_stack(P, 4 * 3001 * 3001, 1, 3001, 3001, P, None, None, None, P, P, 1 << 20, None) == _lib.ERR_ARG   # pitch multiple of 16 fails first
+    assert lib.msl_stage_slices(P, 1, 182, 218, 182, 7, None, None, 182, P, 39680, None) == _lib.ERR_ARG and b"Plano" in lib.msl_last_error()
+    assert lib.msl_stage_slices(P, 1, 182, 218, 182, 0, None, None, 5, P, 39680, None) == _lib.ERR_ARG and b"dense mode" in lib.msl_last_error()
+    assert lib.msl_stage_slices(P, 1, 182, 218, 182, 0, P, P, 5, P, 100, None) == _lib.ERR_ARG and b"pitch" in lib.msl_last_error()
+    assert lib.msl_stage_slices(P, 1, 181, 218, 182, 0, P, P, 5, P, 39680, None) == _lib.ERR_UNSUPPORTED      # odd rows: the slice kernel's job
+    assert lib.msl_stage_slices(P, 1, 182, 218, 182, 0, P, P, 0, P, 39680, None) == 0
+    assert lib.msl_selftest_norm_division(None, None, 4, P, None) == _lib.ERR_ARG
+    # codec: sizes, distances, workspace
+    assert lib.msl_deflate_bound(4, _lib.Z_GZIP, 16384) >= 4 * 16384 and lib.msl_deflate_workspace_bytes(4, _lib.Z_GZIP, 16384) > lib.msl_deflate_bound(4, _lib.Z_GZIP, 16384)
+    assert lib.msl_profile_timeline(0, None, None, None, None) == 0
+
+
 def test_host_box_logic():
     from mslesseg_b200 import ops
     a = np.zeros(10, np.uint8); b = np.zeros(7, np.uint8)
