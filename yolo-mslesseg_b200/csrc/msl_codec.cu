@@ -19,7 +19,7 @@
 //   funnel-shifted, the filter byte shifted in), two staging buffers alternate so that a tile costs three barriers;
 //   16-byte flushes, the carry to the next tile, Adler-32 (dp4a) / CRC-32 (slicing by four from registers + one GF(2)
 //   multiplication per thread) of the raw bytes and the container header / trailer are handled by the same CTA.
-// scan_sizes_kernel + pack_kernel: the variable-length streams are packed back to back (exclusive scan of the sizes) into
+// pack_kernel: the variable-length streams are packed back to back (every CTA sums the sizes in front of its streams) into
 //   one buffer = one D2H copy; PNG's IDAT CRC-32 (over the compressed bytes) is computed during the copy.
 #include <cstring>
 #include <mutex>
@@ -663,36 +663,12 @@ __global__ void __launch_bounds__(kZThreads, 4) deflate_kernel(const ZArgs a) {
     }
 }
 
-// exclusive scan of the stream sizes -> byte offsets of the packed streams.  One CTA: every thread sums a run of consecutive
-// sizes, one block scan of the 1024 partial sums, then the run is written out (n is a few ten thousand at most).
-__global__ void __launch_bounds__(1024) scan_sizes_kernel(const uint32_t* meta, int n, unsigned align, unsigned long long* off) {
-    __shared__ unsigned long long wsum[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (n + 1023) / 1024;
-    const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
-    unsigned long long v = 0;
-    for (int i = i0; i < i1; ++i) v += (((unsigned long long)meta[4 * (size_t)i] + align - 1) / align) * align;
-    unsigned long long inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) wsum[warp] = inc;
-    block_sync();
-    unsigned long long wb = 0, tot = 0;
-    for (int w = 0; w < 32; ++w) { const unsigned long long t = wsum[w]; if (w < warp) wb += t; tot += t; }
-    unsigned long long run = wb + inc - v;
-    for (int i = i0; i < i1; ++i) {
-        off[i] = run;
-        run += (((unsigned long long)meta[4 * (size_t)i] + align - 1) / align) * align;
-    }
-    if (tid == 0) off[n] = tot;
-}
-
 // copies stream s from its slot to out + off[s]; PNG: IDAT length and CRC-32 over (type + compressed data)
 struct PackArgs {
     const uint8_t* slots;
     size_t slot_pitch;
     const uint32_t* meta;
-    const unsigned long long* off;
+    unsigned long long* off;   // [n + 1]: written here (exclusive scan of the sizes)
     uint8_t* out;
     unsigned long long out_cap;
     uint32_t P64[kZThreads];   // x^(8 * 64 * k)
@@ -701,11 +677,11 @@ struct PackArgs {
 };
 
 // one stream: slot -> out + off[s]
-__device__ __forceinline__ void pack_stream(const PackArgs& a, unsigned s, uint32_t (*crc_table)[256], uint32_t* part, uint32_t& s_run) {
+__device__ __forceinline__ void pack_stream(const PackArgs& a, unsigned s, unsigned long long o, uint32_t (*crc_table)[256], uint32_t* part,
+                                            uint32_t& s_run) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint8_t* slot = a.slots + (size_t)s * a.slot_pitch;
     const uint32_t fsize = a.meta[4 * (size_t)s], idat = a.meta[4 * (size_t)s + 3];
-    const unsigned long long o = a.off[s];
     if (o + fsize > a.out_cap) return;                      // the caller compares off[n] with the capacity
     uint8_t* dst = a.out + o;
     uint32_t clen = 0;                                      // PNG: bytes the IDAT CRC covers = "IDAT" + zlib stream
@@ -795,16 +771,38 @@ __device__ __forceinline__ void pack_stream(const PackArgs& a, unsigned s, uint3
 }
 
 // Grid-stride over the streams: a bounded number of CTAs, so that a launch whose destination is mapped HOST memory (the copy
-// then runs at the speed of the host link) leaves most of every SM to the kernels of other CUDA streams.
+// then runs at the speed of the host link) leaves most of every SM to the kernels of other CUDA streams.  Every CTA sums the
+// sizes in front of its streams itself (a few thousand 32-bit loads at most), which saves the scan kernel between deflate and
+// pack - a one-CTA launch that used to queue behind the wide kernels of the other streams.
 __global__ void __launch_bounds__(kZThreads) pack_kernel(const PackArgs a) {
     __shared__ uint32_t crc_table[4][256];
     __shared__ uint32_t part[kZThreads / 32];
     __shared__ uint32_t s_run;
-    crc_tables(crc_table, threadIdx.x);
-    block_sync();
-    for (unsigned s = blockIdx.x; s < (unsigned)a.n; s += gridDim.x) {
-        pack_stream(a, s, crc_table, part, s_run);
+    __shared__ unsigned long long red[kZThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto block_sum = [&](unsigned lo, unsigned hi) -> unsigned long long {          // sum of the sizes of streams [lo, hi)
+        unsigned long long v = 0;
+        for (unsigned j0 = lo; j0 < hi; j0 += kZThreads) if (const unsigned j = j0 + (unsigned)tid; j < hi) v += a.meta[4 * (size_t)j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        block_sync();                                                                 // (red may still be read from the last call)
+        if (lane == 0) red[warp] = v;
         block_sync();
+        unsigned long long t = 0;
+#pragma unroll
+        for (int w = 0; w < kZThreads / 32; ++w) t += red[w];
+        return t;
+    };
+    crc_tables(crc_table, tid);
+    unsigned long long o = block_sum(0, blockIdx.x);
+    for (unsigned s = blockIdx.x; s < (unsigned)a.n; s += gridDim.x) {
+        if (tid == 0) {
+            a.off[s] = o;
+            if (s + 1 == (unsigned)a.n) a.off[s + 1] = o + a.meta[4 * (size_t)s];
+        }
+        pack_stream(a, s, o, crc_table, part, s_run);
+        if (s + gridDim.x < (unsigned)a.n) o += block_sum(s, s + gridDim.x);
+        else block_sync();
     }
 }
 
@@ -916,11 +914,6 @@ int launch_deflate_pack(const uint8_t* src, int n, size_t src_pitch, size_t chun
         ProfScope prof(K_DEFLATE, stream);
         deflate_kernel<<<n, kZThreads, 0, stream>>>(a);
         MSL_LAUNCH_CHECK("deflate_kernel");
-    }
-    {
-        ProfScope prof(K_DEFLATE_SCAN, stream);
-        scan_sizes_kernel<<<1, 1024, 0, stream>>>(a.meta, n, 1u, out_off);
-        MSL_LAUNCH_CHECK("scan_sizes_kernel");
     }
     {
         ProfScope prof(K_DEFLATE_PACK, stream);
