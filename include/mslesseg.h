@@ -179,10 +179,11 @@ int msl_png_pack(const uint8_t* pixels, int n, int H, int W, int channels,
 /* ---- byte-stream codec, encode side: deflate on the device -----------------------
  * Replaces the zlib work behind plt.imsave (scripts/extraer_dataset.py:192,197), cv2.imwrite (utils/utils.py:393,
  * scripts/generar_predicciones.py:153) and nib.save (utils/utils.py:176-177): what crosses PCIe and lands on disk are the
- * compressed files.  A stream is a sequence of deflate blocks (RFC 1951) of two kinds, chosen per 2 KB of input: stored
- * blocks for bytes that do not repeat (a fixed Huffman code cannot shrink them) and fixed-Huffman blocks holding run
- * matches at ONE distance `dist2` in 1..4 (0 means 1: repeated bytes; 4 suits RGBA pixels and float32 voxels: repeated
- * elements) for 64-byte segments that lie inside a run; the last block is an empty stored block.  Inside the container
+ * compressed files.  A stream is a sequence of deflate blocks (RFC 1951) of two kinds, chosen per 16-byte segment inside
+ * tiles of 4 KB: stored blocks for bytes that do not repeat (a fixed Huffman code cannot shrink them) and fixed-Huffman
+ * blocks holding run matches at ONE distance `dist2` in 1..4 (0 means 1: repeated bytes; 4 suits RGBA pixels and float32
+ * voxels: repeated elements) for segments that lie inside a run; the last block is an empty stored block.  Any inflate
+ * implementation reads the result (the tests decode every stream with zlib / gzip / Pillow).  Inside the container
  * asked for:
  *   MSL_Z_RAW   bare deflate            MSL_Z_ZLIB  RFC 1950 (0x78 0x01, Adler-32)
  *   MSL_Z_GZIP  RFC 1952 member; header carries an FEXTRA subfield 'M','S' = {u32 member bytes, u32 raw bytes}, so a
