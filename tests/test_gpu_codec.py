@@ -292,3 +292,33 @@ def test_own_streams_round_trip_all_distances(ops, codec, cuda_device):
                 host = out.cpu().numpy()
                 got = np.concatenate([host[o[i]:o[i] + meta[i, 1]] for i in range(len(pieces))]) if len(pieces) else np.zeros(0, np.uint8)
                 assert np.array_equal(got, data), (container, name, chunk, d2)
+
+
+def test_run_groups_of_every_length(ops, cuda_device):
+    """A run group of k segments (k = 1 .. 256: one fixed block of 258-byte matches + the rest, 1808 bytes being the case whose
+    rest would be two bytes) between literal segments, at every position class of a 4 KB tile and across tile borders:
+    zlib on the host decodes what the device wrote."""
+    import torch
+    rng = np.random.default_rng(77)
+    streams, chunk = [], 3 * 4096
+    for k in list(range(1, 257)) + [113, 113, 256, 255, 17, 33]:
+        for d, lead in ((1, int(rng.integers(0, 40))), (4, int(rng.integers(0, 40)))):
+            buf = rng.integers(1, 255, chunk, dtype=np.uint8)
+            # literal bytes that never repeat at distance d inside a segment (so that only the planted run is a run)
+            buf[::2] = (np.arange(chunk // 2) * 7 + 3) % 251 + 1
+            a = 16 * lead
+            b = min(a + 16 * k, chunk)
+            pattern = rng.integers(1, 255, d, dtype=np.uint8)
+            buf[a:b] = np.resize(pattern, b - a)
+            if a >= d:
+                buf[a - d:a] = pattern                      # the run has something to refer back to
+            streams.append((d, buf))
+    for d in (1, 4):
+        data = np.concatenate([b for dd, b in streams if dd == d])
+        for container in ("zlib", "gzip"):
+            ps = ops.deflate_chunks(torch.from_numpy(data).to(cuda_device), chunk_len=chunk, container=container, dist2=d)
+            packed, off = ps.to_host()
+            back = b"".join((zlib.decompress(packed[off[i]:off[i + 1]].tobytes()) if container == "zlib"
+                             else gzip.decompress(packed[off[i]:off[i + 1]].tobytes())) for i in range(len(off) - 1))
+            assert back == data.tobytes(), (d, container)
+            assert off[-1] < data.size                                   # the planted runs were found
