@@ -142,6 +142,25 @@ def test_inflate_decodes_zlib_gzip_and_own_streams(ops, codec, cuda_device):
     out, off = codec.inflate([blob[p:p + m] for p, m, _ in members], [r for _, _, r in members], "gzip", cuda_device)
     got = np.concatenate([out.cpu().numpy()[off[i]:off[i] + members[i][2]] for i in range(len(members))])
     assert np.array_equal(got, pl["float32"])
+    # far matches (a 20 KB block repeated: distances beyond the 2 KB output ring, served from global memory), overlapping
+    # short-period matches of every period 1..9, and a gzip header with FEXTRA + FNAME + FCOMMENT + FHCRC
+    rng = np.random.default_rng(9)
+    block = rng.integers(0, 256, 20_000, dtype=np.uint8)
+    far = np.concatenate([block, block, block[:7000], rng.integers(0, 256, 3000, dtype=np.uint8), block[5000:]])
+    periods = np.concatenate([np.resize(rng.integers(0, 256, p_, dtype=np.uint8), 3000 + 37 * p_) for p_ in range(1, 10)])
+    for data in (far, periods):
+        for level in (1, 6, 9):
+            out, off = codec.inflate([zlib.compress(data.tobytes(), level)], [data.size], "zlib", cuda_device)
+            assert np.array_equal(out.cpu().numpy()[:data.size], data), (data.size, level)
+    raw_member = zlib.compressobj(6, zlib.DEFLATED, -15)
+    body = raw_member.compress(far.tobytes()) + raw_member.flush()
+    hdr = bytearray(b"\x1f\x8b\x08\x1e\x00\x00\x00\x00\x00\xff")                       # FLG = FEXTRA | FNAME | FCOMMENT | FHCRC
+    hdr += struct.pack("<H", 6) + b"XX\x02\x00ab" + b"name.nii\x00" + b"a comment\x00"
+    hdr += struct.pack("<H", zlib.crc32(bytes(hdr)) & 0xffff)
+    member = bytes(hdr) + body + struct.pack("<II", zlib.crc32(far.tobytes()), far.size)
+    assert gzip.decompress(member) == far.tobytes()
+    out, off = codec.inflate([member], [far.size], "gzip", cuda_device)
+    assert np.array_equal(out.cpu().numpy()[:far.size], far)
     # damaged input is reported, not decoded
     bad = bytearray(zlib.compress(pl["mixed"].tobytes(), 6))
     bad[40] ^= 0x55
