@@ -433,7 +433,7 @@ __device__ __forceinline__ uint4 load_seg(const ZArgs& a, const uint8_t* __restr
 }
 
 
-__global__ void __launch_bounds__(kZThreads, 4) deflate_kernel(const ZArgs a) {
+__global__ void __launch_bounds__(kZThreads, 5) deflate_kernel(const ZArgs a) {
     __shared__ __align__(16) uint8_t Xs[kLook + kTile + 4 * (kZThreads + 2) + 16];
     __shared__ __align__(16) uint8_t Ys2[2][kYBytes + 16];
     __shared__ uint32_t crc_table[4][256];            // slicing by four: table k = a byte followed by k zero bytes
