@@ -43,7 +43,7 @@ constexpr int kTile = kZThreads * kSeg;          // 4 KB
 constexpr int kLook = 16;                        // look-back kept in front of the tile (>= the largest match distance)
 constexpr int kYBytes = 16 + kTile + kTile / 2 + 128;   // staging: carry + worst case (every other 16-byte segment its own stored block) + trailer
 constexpr uint32_t kCrcPoly = 0xedb88320u;       // reflected CRC-32 polynomial
-constexpr int kTmplBytes = 400;                  // stream of an all-zero chunk of up to four tiles (378 bytes as a gzip member)
+constexpr int kTmplBytes = kZeroTmplBytes;       // stream of an all-zero chunk of up to four tiles (190 bytes as a gzip member)
 
 // a * b mod P over GF(2), operands in the reflected representation CRC-32 uses (bit 31 = x^0)
 __host__ __device__ inline uint32_t gf_mul(uint32_t a, uint32_t b) {
@@ -856,6 +856,12 @@ void zero_chunk_stream(int container, int d, unsigned n, uint32_t meta[4], uint8
     cache.push_back(e);
     memcpy(meta, e.meta, sizeof(e.meta)); memcpy(out, e.bytes, kTmplBytes);
 }
+
+}  // namespace
+
+void zero_chunk_gzip(int d, unsigned n, uint32_t meta[4], uint8_t* out) { zero_chunk_stream(MSL_Z_GZIP, d, n, meta, out); }
+
+namespace {
 
 inline size_t raw_len_of(size_t chunk, int rows, int row_bytes) { return rows > 0 ? (size_t)rows * ((size_t)row_bytes + 1) : chunk; }
 

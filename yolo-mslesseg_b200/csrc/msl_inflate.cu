@@ -49,6 +49,10 @@ struct InfArgs {
     uint32_t* status;                    // [n][4]: error, bytes produced, stored checksum (Adler-32 / CRC-32 of the last member), stored ISIZE
     int n, container;
     unsigned long long src_bytes;        // readable bytes at src (loads are clamped to it)
+    // gzip members this library writes for an all-zero 16 KB chunk (one per match distance): a member whose bytes equal one of
+    // them decodes to zeros without being decoded
+    uint32_t tmpl[4][kZeroTmplBytes / 4];
+    uint32_t tmpl_size[4], tmpl_chk[4], tmpl_raw;
 };
 
 enum { INF_OK = 0, INF_ERR_HEADER = 1, INF_ERR_BLOCK = 2, INF_ERR_CODE = 3, INF_ERR_DIST = 4, INF_ERR_SPACE = 5, INF_ERR_INPUT = 6 };
@@ -218,6 +222,29 @@ __global__ void __launch_bounds__(kInfWarps * 32) inflate_kernel(const InfArgs a
         __syncwarp();
     };
 
+    if (a.container == MSL_Z_GZIP && a.tmpl_raw && cap >= a.tmpl_raw) {
+        const unsigned long long msize = send - sbeg;
+        for (int k = 0; k < 4; ++k) {
+            if (msize != a.tmpl_size[k]) continue;                                  // (warp-uniform)
+            bool eq = true;
+            const uint8_t* t = reinterpret_cast<const uint8_t*>(a.tmpl[k]);
+            for (unsigned j = lane; j < (unsigned)msize; j += 32) eq = eq && a.src[sbeg + j] == t[j];
+            if (!__all_sync(FULL, eq)) continue;
+            const unsigned raw = a.tmpl_raw;
+            if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+                uint4* o4 = reinterpret_cast<uint4*>(out);
+                for (unsigned q = lane; q < (raw >> 4); q += 32) o4[q] = make_uint4(0, 0, 0, 0);
+                for (unsigned q = (raw & ~15u) + lane; q < raw; q += 32) out[q] = 0;
+            } else {
+                for (unsigned q = lane; q < raw; q += 32) out[q] = 0;
+            }
+            if (lane == 0) {
+                uint32_t* st = a.status + 4 * (size_t)s;
+                st[0] = INF_OK; st[1] = raw; st[2] = a.tmpl_chk[k]; st[3] = raw;
+            }
+            return;
+        }
+    }
     for (;;) {      // members (gzip files may hold several)
         // ---- container header
         if (a.container == MSL_Z_ZLIB) {
@@ -702,6 +729,15 @@ int launch_inflate(const uint8_t* src, size_t src_bytes, const unsigned long lon
     InfArgs a;
     a.src = src; a.src_off = src_off; a.dst = dst; a.dst_off = dst_off; a.status = status; a.n = n; a.container = container;
     a.src_bytes = src_bytes;
+    a.tmpl_raw = 0;
+    if (container == MSL_Z_GZIP) {
+        for (int k = 0; k < 4; ++k) {
+            uint32_t meta[4];
+            zero_chunk_gzip(k + 1, 16384u, meta, reinterpret_cast<uint8_t*>(a.tmpl[k]));
+            a.tmpl_size[k] = meta[0]; a.tmpl_chk[k] = meta[2];
+        }
+        a.tmpl_raw = 16384u;
+    }
     ProfScope prof(K_INFLATE, stream);
     inflate_kernel<<<(n + kInfWarps - 1) / kInfWarps, kInfWarps * 32, 0, stream>>>(a);
     MSL_LAUNCH_CHECK("inflate_kernel");

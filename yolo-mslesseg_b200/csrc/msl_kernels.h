@@ -128,6 +128,10 @@ int launch_png_pack(const uint8_t* pixels, int n, int H, int W, int ch, uint8_t*
 // msl_codec.cu: deflate streams in zlib / gzip / PNG containers, packed back to back
 size_t deflate_slot_bytes(int container, size_t raw);
 size_t deflate_workspace_bytes(int n, int container, size_t raw);
+// the gzip member deflate_kernel writes for a chunk of n zero bytes at match distance d (n = 1..4 whole 4 KB tiles): meta =
+// {member bytes, n, CRC-32, 0}, bytes into out[kZeroTmplBytes] (host side, cached)
+constexpr int kZeroTmplBytes = 400;
+void zero_chunk_gzip(int d, unsigned n, uint32_t meta[4], uint8_t* out);
 int launch_deflate_pack(const uint8_t* src, int n, size_t src_pitch, size_t chunk, size_t total, int rows, int row_bytes,
                         int img_w, int img_ch, int container, int dist2, const uint8_t* prefix, size_t prefix_pitch, size_t prefix_len,
                         int expand, uint8_t* out, size_t out_cap, unsigned long long* out_off,
